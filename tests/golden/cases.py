@@ -1,0 +1,53 @@
+"""
+Golden-fixture case table shared by make_golden.py (which runs the REAL
+reference from /root/reference in the build container) and the tests (which
+check oracle/ and the CUDA path against the committed fixtures).
+"""
+
+TINY = dict(depth=4, dim=32, heads=2, mlp_ratio=4, position_encoding_size=(4, 4),
+            window_indices=(0, 2), window_size=(4, 4), relative_embedding_size=(5, 5))
+TINY_GLOBAL = dict(depth=2, dim=32, heads=2, mlp_ratio=4, position_encoding_size=(4, 4))
+SMALL_B = dict(depth=3, dim=768, heads=12, mlp_ratio=4, position_encoding_size=(14, 14),
+               window_indices=(0, 2), window_size=(14, 14), relative_embedding_size=(64, 64))
+
+CASES = {
+    # windowed (padded 7->8) + global eventful blocks, rel-pos with interpolated tables
+    "tiny_vitdet": dict(cfg=TINY, input_size=(7, 7), batch=1, frames=5, policy=("topk", dict(k=12)),
+                        block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
+                        std=0.08, stream="drift", seed=1),
+    # batch > 1, class token, no windows / rel-pos (the ViViT spatial sub-model shape)
+    "tiny_vivit": dict(cfg=TINY_GLOBAL, input_size=(4, 4), batch=3, frames=4, policy=("topk", dict(k=5)),
+                       block_class="EventfulBlock", has_class_token=True, std=0.08, stream="drift", seed=2),
+    "tiny_matmul1": dict(cfg=TINY_GLOBAL, input_size=(4, 4), batch=2, frames=4, policy=("topk", dict(k=6)),
+                         block_class="EventfulMatmul1Block", std=0.08, stream="drift", seed=3),
+    "tiny_tokenwise": dict(cfg=TINY_GLOBAL, input_size=(4, 4), batch=2, frames=4, policy=("topk", dict(k=6)),
+                           block_class="EventfulTokenwiseBlock", std=0.08, stream="drift", seed=4),
+    "tiny_threshold": dict(cfg=TINY, input_size=(7, 7), batch=1, frames=4,
+                           policy=("threshold", dict(threshold=1.0)),
+                           block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
+                           std=0.08, stream="patch", seed=5),
+    "tiny_fraction": dict(cfg=TINY_GLOBAL, input_size=(4, 4), batch=1, frames=3,
+                          policy=("fraction", dict(fraction=0.4)),
+                          block_class="EventfulBlock", std=0.08, stream="drift", seed=6),
+    "tiny_cast": dict(cfg=TINY, input_size=(7, 7), batch=1, frames=4, policy=("topk", dict(k=12)),
+                      block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
+                      matmul_2_cast="bfloat16", std=0.08, stream="drift", seed=7),
+    "tiny_gate_before_ln": dict(cfg=TINY_GLOBAL, input_size=(4, 4), batch=1, frames=4,
+                                policy=("topk", dict(k=6)), block_class="EventfulBlock",
+                                gate_before_ln=True, std=0.08, stream="drift", seed=8),
+    "tiny_stgt": dict(cfg=TINY_GLOBAL, input_size=(4, 4), batch=1, frames=4, policy=("topk", dict(k=6)),
+                      block_class="EventfulTokenwiseBlock", stgt=True, std=0.08, stream="drift", seed=9),
+    "tiny_dense": dict(cfg=TINY, input_size=(7, 7), batch=2, frames=2, policy=None,
+                       block_class="Block", windowed_class=None, std=0.08, stream="drift", seed=10),
+    # real ViTDet-B widths (D=768, H=12, 14x14 windows padded 16->28, 64-entry rel tables interpolated)
+    "small_vitdet_b": dict(cfg=SMALL_B, input_size=(16, 16), batch=1, frames=3, policy=("topk", dict(k=64)),
+                           block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
+                           std=0.04, stream="drift", seed=11, subsample=True),
+}
+
+GATES = ("qkv_gate", "projection_gate", "mlp_gate")
+
+
+def n_tokens(case):
+    h, w = case["input_size"]
+    return h * w + int(case.get("has_class_token", False))
