@@ -1,0 +1,380 @@
+// Gathered-row linear with scatter epilogue on 5th-gen tensor cores (sm_100a).
+//
+//   y = act(A @ W^T + bias);   out[scatter_row(m), :] = y[m, :]
+//
+// Warp-specialised, one 128 x BLOCK_N output tile per CTA:
+//   warp 0    : TMA producer   (cp.async.bulk.tensor 2-D, 128-byte swizzle, K slices of 64)
+//   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, fp32 accumulate in TMEM)
+//   warps 2-5 : epilogue       (tcgen05.ld 32 lanes x 32 columns -> bias / GELU -> 16-byte row stores,
+//                               rows redirected through the gate's index = TokenBuffer scatter)
+// smem ring of STAGES {A 128x64, W BLOCK_Nx64} tiles guarded by full/empty mbarriers; the MMA warp
+// releases a stage with tcgen05.commit and signals the epilogue through a third barrier.
+// TMA out-of-bounds zero fill handles the M / n_feat / K tails, so any M, K % 8 == 0 and
+// n_feat % 8 == 0 are accepted.
+#include <cuda.h>
+
+#include "et_common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 x 16-bit = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+struct LinearArgs {
+    const void* bias;
+    void* out;
+    const long long* idx;
+    const int* count;
+    long long ld_out;
+    int M, K, n_feat, act, k, n_out_rows, is_bf16;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long start = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - start > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_load_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile with 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);        // start address        bits [0,14)
+    d |= (uint64_t)1 << 16;                             // leading byte offset  bits [16,30) (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset   bits [32,46)
+    d |= (uint64_t)1 << 46;                             // descriptor version = 1 (sm_100)
+    d |= (uint64_t)2 << 61;                             // layout type 2 = SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major, M = 128, N = BLOCK_N.
+__device__ __forceinline__ uint32_t umma_idesc(int n, int is_bf16) {
+    uint32_t d = 0;
+    d |= 1u << 4;                          // c_format = F32
+    d |= (is_bf16 ? 1u : 0u) << 7;         // a_format
+    d |= (is_bf16 ? 1u : 0u) << 10;        // b_format
+    d |= (uint32_t)(n >> 3) << 17;         // n_dim
+    d |= (uint32_t)(BLOCK_M >> 4) << 24;   // m_dim
+    return d;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+template <int BLOCK_N, int STAGES>
+struct GemmSmem {
+    static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                      const LinearArgs args) {
+    using L = GemmSmem<BLOCK_N, STAGES>;
+    constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tmem_full_bar = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BLOCK_N;
+    const int m0 = blockIdx.y * BLOCK_M;
+    const int num_k_blocks = (args.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(tmem_full_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // whole warp: allocate the accumulator columns, then let other CTAs allocate
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t parity = (kb / STAGES) & 1;
+                mbar_wait(smem_u32(&empty_bar[s]), parity ^ 1);
+                const uint32_t a_dst = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint32_t fb = smem_u32(&full_bar[s]);
+                mbar_expect_tx(fb, L::STAGE_BYTES);
+                tma_load_2d(a_dst, &tmap_a, fb, kb * BLOCK_K, m0);
+                tma_load_2d(a_dst + A_TILE_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(BLOCK_N, args.is_bf16);
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t parity = (kb / STAGES) & 1;
+                mbar_wait(smem_u32(&full_bar[s]), parity);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint64_t da = umma_smem_desc(a_addr);
+                const uint64_t db = umma_smem_desc(a_addr + A_TILE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                    // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+                    tcgen05_mma_f16(tmem_base, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc,
+                                    (kb > 0 || kk > 0) ? 1u : 0u);
+                }
+                tcgen05_commit(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs retire
+            }
+            tcgen05_commit(smem_u32(tmem_full_bar));  // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warp w may only touch TMEM lanes [32 * (w % 4), +32)
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int m = m0 + row;
+        bool valid = m < args.M;
+        long long out_row = m;
+        if (valid && args.idx != nullptr) {
+            const int b = m / args.k, j = m - b * args.k;
+            if (args.count != nullptr && j >= args.count[b]) valid = false;
+            if (valid) out_row = (long long)b * args.n_out_rows + args.idx[m];
+        }
+        mbar_wait(smem_u32(tmem_full_bar), 0);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            uint32_t acc[32];
+            __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned): reconverge after the guarded stores
+            tmem_load_32x32(taddr + (uint32_t)c0, acc);
+            const int n = n0 + c0;
+            if (valid && n < args.n_feat) {
+            uint4 packed[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int ng = n + g * 8;
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(acc[g * 8 + i]);
+                if (ng < args.n_feat) {
+                    if (args.bias != nullptr) {
+                        float bv[8];
+                        const uint4 braw = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(args.bias) + ng);
+                        if (args.is_bf16) unpack16<__nv_bfloat16>(braw, bv);
+                        else unpack16<__half>(braw, bv);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) y[i] += bv[i];
+                    }
+                    if (args.act == ET_ACT_GELU) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) y[i] = gelu_erf(y[i]);
+                    }
+                }
+                packed[g] = args.is_bf16 ? pack16<__nv_bfloat16>(y) : pack16<__half>(y);
+            }
+            uint16_t* dst = static_cast<uint16_t*>(args.out) + out_row * args.ld_out + n;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (n + g * 8 < args.n_feat) st16(dst + g * 8, packed[g]);
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D row-major (rows, cols) 16-bit tensor, box (box_rows, 64 cols), 128-byte swizzle
+int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int is_bf16) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return et_fail(ET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return et_fail(ET_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return ET_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+int launch_linear(const void* A, const void* W, const LinearArgs& args, cudaStream_t stream) {
+    using L = GemmSmem<BLOCK_N, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tcgen05_kernel<BLOCK_N, STAGES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        if (e != cudaSuccess) return et_fail(ET_ERR_CUDA, "et_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    CUtensorMap ta, tw;
+    int rc = make_tmap(&ta, A, args.M, args.K, BLOCK_M, args.is_bf16);
+    if (rc) return rc;
+    rc = make_tmap(&tw, W, args.n_feat, args.K, BLOCK_N, args.is_bf16);
+    if (rc) return rc;
+    dim3 grid((args.n_feat + BLOCK_N - 1) / BLOCK_N, (args.M + BLOCK_M - 1) / BLOCK_M);
+    linear_tcgen05_kernel<BLOCK_N, STAGES><<<grid, kGemmThreads, L::TOTAL, stream>>>(ta, tw, args);
+    return ET_OK;
+}
+
+int g_force_block_n = 0;  // test hook: et_debug_set(1, BLOCK_N)
+
+}  // namespace
+
+extern "C" {
+
+int et_debug_set(int key, long long value) {
+    if (key == 1) {
+        g_force_block_n = (int)value;
+        return ET_OK;
+    }
+    return et_fail(ET_ERR_ARG, "et_debug_set: unknown key %d", key);
+}
+
+int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bias, int64_t n_feat, int act, void* out,
+              int64_t ld_out, const int64_t* idx, const int32_t* count, int64_t k, int64_t n_out_rows, int dtype,
+              void* stream) {
+    ET_CHECK_ARG(A && W && out, "et_linear: null pointer");
+    ET_CHECK_ARG(dtype == ET_BF16 || dtype == ET_F16,
+                 "et_linear: the tcgen05 path computes in bf16/fp16 with fp32 accumulation (dtype=%d)", dtype);
+    ET_CHECK_ARG(M >= 0 && K > 0 && n_feat > 0 && M < (1LL << 31) && K % 8 == 0 && n_feat % 8 == 0 && ld_out % 8 == 0,
+                 "et_linear: need K, n_feat, ld_out multiples of 8 (M=%lld K=%lld n_feat=%lld ld_out=%lld)",
+                 (long long)M, (long long)K, (long long)n_feat, (long long)ld_out);
+    ET_CHECK_ARG(et_aligned16(A) && et_aligned16(W) && et_aligned16(out) && et_aligned16(bias),
+                 "et_linear: pointers must be 16-byte aligned");
+    ET_CHECK_ARG(act == ET_ACT_NONE || act == ET_ACT_GELU, "et_linear: unknown activation %d", act);
+    if (idx != nullptr) ET_CHECK_ARG(k > 0 && M % k == 0 && n_out_rows > 0, "et_linear: scatter needs k | M and n_out_rows");
+    ET_CHECK_ARG(count == nullptr || idx != nullptr, "et_linear: count needs idx");
+    if (M == 0) return ET_OK;
+    LinearArgs a;
+    a.bias = bias; a.out = out; a.idx = reinterpret_cast<const long long*>(idx); a.count = count; a.ld_out = ld_out;
+    a.M = (int)M; a.K = (int)K; a.n_feat = (int)n_feat; a.act = act; a.k = (int)(idx ? k : 1);
+    a.n_out_rows = (int)n_out_rows; a.is_bf16 = dtype == ET_BF16;
+
+    // Tile width: minimise waves(tiles over 148 SMs) x per-tile cost (~ BLOCK_N + fixed overhead).
+    const int candidates[5] = {256, 192, 128, 96, 64};
+    int best = 64;
+    double best_cost = 1e30;
+    const long long mt = (M + BLOCK_M - 1) / BLOCK_M;
+    for (int c = 0; c < 5; ++c) {
+        const int bn = candidates[c];
+        if (bn > 64 && bn >= 2 * n_feat) continue;
+        const long long tiles = mt * ((n_feat + bn - 1) / bn);
+        const double cost = (double)((tiles + 147) / 148) * (bn + 32);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    }
+    if (g_force_block_n) best = g_force_block_n;
+    int rc;
+    cudaStream_t s = et_stream(stream);
+    switch (best) {
+        case 256: rc = launch_linear<256, 4>(A, W, a, s); break;
+        case 192: rc = launch_linear<192, 5>(A, W, a, s); break;
+        case 128: rc = launch_linear<128, 6>(A, W, a, s); break;
+        case 96: rc = launch_linear<96, 7>(A, W, a, s); break;
+        case 64: rc = launch_linear<64, 8>(A, W, a, s); break;
+        default: return et_fail(ET_ERR_ARG, "et_linear: unsupported BLOCK_N %d", best);
+    }
+    if (rc) return rc;
+    ET_CHECK_LAUNCH("et_linear");
+    return ET_OK;
+}
+
+}  // extern "C"

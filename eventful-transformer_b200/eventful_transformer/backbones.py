@@ -1,0 +1,108 @@
+"""
+ViTBackbone: position encoding + a sequence of blocks chosen by class name
+(API mirror of the reference's backbones.py:8-64; same kwargs and state-dict keys).
+
+Steady-state frames can be replayed from a CUDA graph: every kernel of the gated path is enqueued
+through the C ABI on the current stream without host synchronisation (top-k policies), so one
+incremental frame is a fixed launch sequence over persistent state tensors.
+"""
+
+import os
+
+import torch
+import torch.nn as nn
+
+from eventful_transformer import _native as native
+from eventful_transformer import blocks
+from eventful_transformer.base import ExtendedModule
+from eventful_transformer.modules import SimpleSTGTGate, TokenDeltaGate, TokenGate, _policy_spec
+from eventful_transformer.utils import PositionEncoding
+
+
+class ViTBackbone(ExtendedModule):
+    """Common backbone for vision Transformers."""
+
+    def __init__(self, block_config, depth, position_encoding_size, input_size, block_class="Block",
+                 has_class_token=False, window_indices=(), windowed_class=None, windowed_overrides=None):
+        super().__init__()
+        self.position_encoding = PositionEncoding(
+            block_config["dim"], position_encoding_size, input_size, has_class_token)
+        self.blocks = nn.Sequential()
+        for i in range(depth):
+            name = block_class
+            config = dict(block_config)
+            if i in window_indices:
+                if windowed_class is not None:
+                    name = windowed_class
+                if windowed_overrides is not None:
+                    config.update(windowed_overrides)
+            else:
+                config["window_size"] = None
+            self.blocks.append(getattr(blocks, name)(input_size=input_size, **config))
+        # CUDA-graph replay of incremental frames (opt-in: attribute or EVENTFUL_B200_GRAPH=1)
+        self.use_cuda_graph = os.environ.get("EVENTFUL_B200_GRAPH", "0") == "1"
+        self._graph = None
+        self._graph_key = None
+        self._static_in = None
+        self._static_out = None
+        self._frames_seen = 0
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x):
+        native.require_device(x)
+        x = x.contiguous()
+        if self.use_cuda_graph and self._graphable(x):
+            return self._forward_graph(x)
+        self._frames_seen += 1
+        return self._forward_eager(x)
+
+    def _forward_eager(self, x):
+        pos = self.position_encoding
+        if pos.count_mode:
+            pos.add.counts["add_flops"] += x.numel()
+        xa, xb = x, pos.sized_encoding(x.shape[0])
+        if xb.dtype != x.dtype:
+            raise TypeError(f"position encoding is {xb.dtype} but the input is {x.dtype}; cast the model or the input")
+        for block in self.blocks:
+            xa, xb = block._forward_pair(xa, xb)
+        return native.add(xa, xb)
+
+    def reset_self(self):
+        self._graph = None
+        self._graph_key = None
+        self._static_in = None
+        self._static_out = None
+        self._frames_seen = 0
+
+    # ------------------------------------------------------------------ CUDA graph replay
+    def _policy_key(self, n_tokens):
+        key = []
+        for gate in self.modules_of_type((TokenGate, TokenDeltaGate, SimpleSTGTGate)):
+            spec = _policy_spec(gate.policy, n_tokens) if gate.policy is not None else None
+            if gate.policy is not None and (spec is None or "threshold" in spec):
+                return None  # data-dependent shapes / user code: not capturable
+            key.append(None if spec is None else spec["k"])
+        return tuple(key)
+
+    def _graphable(self, x):
+        if self.training or self.count_mode or self._frames_seen < 2:
+            return False  # frame 0 is the dense flush, frame 1 warms up the incremental path
+        if any(m.count_mode for m in self.extended_modules()):
+            return False
+        return self._policy_key(x.shape[-2]) is not None
+
+    def _forward_graph(self, x):
+        key = (tuple(x.shape), x.dtype, x.device, self._policy_key(x.shape[-2]))
+        if self._graph is None or self._graph_key != key:
+            self._static_in = torch.empty_like(x)
+            self._static_in.copy_(x)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                self._static_out = self._forward_eager(self._static_in)
+            self._graph, self._graph_key = graph, key
+        else:
+            self._static_in.copy_(x)
+        self._graph.replay()
+        self._frames_seen += 1
+        return self._static_out.clone()

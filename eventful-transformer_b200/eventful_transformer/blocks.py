@@ -1,0 +1,395 @@
+"""
+Transformer blocks: Block, EventfulTokenwiseBlock, EventfulMatmul1Block, EventfulBlock
+(API mirror of the reference's blocks.py: same constructor kwargs, sub-module names and
+state-dict keys, resolvable by name from backbones.ViTBackbone).
+
+How a gated block runs here (incremental frame), per gate site:
+    et_gate_select   [residual add] + LayerNorm + (c - p) + token norm + radix top-k, one launch
+    et_gate_gather   c~ = LN(x)[idx], p[idx] = c~
+    et_linear        tcgen05 GEMM on the k gathered rows, rows scattered into the TokenBuffer
+and for attention
+    et_window_attention   windowed blocks (dense, blocks.py:205-240 of the reference)
+    et_global_attention   global blocks: softmax statistics + A-gate / v-gate / delta accumulation
+A block hands its output to the next one as an un-summed pair (branch, skip) so that the residual
+add is fused into the next gate's load; Block.forward(x) is still the ordinary stand-alone call.
+
+Not implemented yet (reference features outside the round-1 scope): adaptive
+token sampling (ats_fraction), K/V pooling (pool_size), drop-path in training mode.
+"""
+
+from math import prod, sqrt
+
+import torch
+import torch.nn as nn
+
+from eventful_transformer import _native as native
+from eventful_transformer.base import ExtendedModule, numeric_tuple
+from eventful_transformer.counting import CountedAdd, CountedLinear, CountedMatmul
+from eventful_transformer.modules import (
+    MatmulBuffer,
+    MatmulDeltaAccumulator,
+    SimpleSTGTGate,
+    TokenBuffer,
+    TokenDeltaGate,
+    TokenGate,
+    _policy_spec,
+)
+from eventful_transformer.utils import DropPath, RelativePositionEmbedding
+
+LN_EPS = 1e-6
+
+# single-pass attention kernel is used for dense attention over at most this many keys
+_SMALL_ATTENTION = 512
+
+_identity_cache = {}
+
+
+def _identity_index(batch, n, device):
+    key = (batch, n, device)
+    idx = _identity_cache.get(key)
+    if idx is None:
+        idx = torch.arange(n, device=device, dtype=torch.int64).repeat(batch, 1).contiguous()
+        _identity_cache[key] = idx
+    return idx
+
+
+class Block(ExtendedModule):
+    """Dense (non-eventful) Transformer block with optional windowed attention and rel-pos bias."""
+
+    def __init__(self, dim, heads, input_size, mlp_ratio, ats_fraction=None, drop_path_rate=0.0,
+                 relative_embedding_size=None, matmul_2_cast=None, pool_size=None, window_size=None):
+        super().__init__()
+        self.heads = heads
+        self.input_size = tuple(input_size)
+        if ats_fraction is not None:
+            assert pool_size is None
+            assert window_size is None
+            assert not (ats_fraction < 0.0 or ats_fraction > 1.0)
+            raise NotImplementedError("eventful_b200: adaptive token sampling (ats_fraction) is not implemented yet")
+        assert not (drop_path_rate < 0.0 or drop_path_rate > 1.0)
+        assert matmul_2_cast in [None, "float16", "bfloat16"]
+        self.ats_fraction = ats_fraction
+        self.last_ats_indices = None
+        self.matmul_2_cast = matmul_2_cast
+        if pool_size is not None:
+            raise NotImplementedError("eventful_b200: K/V pooling (pool_size) is not implemented yet")
+        self.pool_size = None
+        if window_size is None:
+            self.window_size = None
+            attention_size = self.input_size
+        else:
+            self.window_size = numeric_tuple(window_size, length=2)
+            attention_size = self.window_size
+            if relative_embedding_size is not None:
+                relative_embedding_size = self.window_size
+        self.scale = sqrt(dim // heads)
+        self.dim = dim
+
+        self.input_layer_norm = nn.LayerNorm(dim, eps=LN_EPS)
+        self.qkv = CountedLinear(in_features=dim, out_features=dim * 3)
+        self.drop_path = DropPath(drop_path_rate) if drop_path_rate > 0.0 else nn.Identity()
+        if relative_embedding_size is not None:
+            self.relative_position = RelativePositionEmbedding(
+                attention_size, tuple(relative_embedding_size), dim // heads, pool_size=None)
+        else:
+            self.relative_position = None
+        self.matmul = CountedMatmul()
+        self.projection = CountedLinear(in_features=dim, out_features=dim)
+        self.add = CountedAdd()
+        self.mlp_layer_norm = nn.LayerNorm(dim, eps=LN_EPS)
+        self.mlp_1 = CountedLinear(in_features=dim, out_features=dim * mlp_ratio)
+        self.gelu = nn.GELU()
+        self.mlp_2 = CountedLinear(in_features=dim * mlp_ratio, out_features=dim)
+
+    # ------------------------------------------------------------------ public forward
+    def forward(self, x):
+        branch, skip = self._forward_pair(x.contiguous(), None)
+        return native.add(branch, skip)
+
+    def reset_self(self):
+        self.last_ats_indices = None
+
+    # ------------------------------------------------------------------ shared helpers
+    def _check_input(self, x):
+        native.require_device(x)
+        if self.training and isinstance(self.drop_path, DropPath):
+            raise NotImplementedError("eventful_b200 is an inference path: drop-path is identity (call .eval())")
+        cast = self.matmul_2_cast
+        if cast is not None and getattr(torch, cast) != x.dtype:
+            raise NotImplementedError(
+                f"eventful_b200: matmul_2_cast='{cast}' on a {x.dtype} model is not implemented; the attention "
+                "kernels run in the model dtype (use model.to(torch.bfloat16) with matmul_2_cast None/'bfloat16')")
+
+    @staticmethod
+    def _ln_params(ln):
+        return ln.weight.detach(), ln.bias.detach()
+
+    def _layer_norm_all(self, ln, x):
+        """Dense LayerNorm over every token (rows gathered with the identity index)."""
+        idx = _identity_index(x.shape[0], x.shape[1], x.device)
+        out, _ = native.gate_gather(x, idx, ln=self._ln_params(ln), eps=ln.eps)
+        return out
+
+    def _count_adds(self, x):
+        if self.count_mode:  # both residual adds of this block (the second is fused downstream)
+            self.add.counts["add_flops"] += 2 * x.numel()
+
+    def _rel_tables(self, dtype):
+        if self.relative_position is None:
+            return None
+        y_rel, x_rel = self.relative_position.tables()
+        if y_rel.dtype != dtype:
+            y_rel, x_rel = y_rel.to(dtype), x_rel.to(dtype)
+        return y_rel, x_rel
+
+    def _window_grid(self):
+        wh, ww = self.window_size
+        gh, gw = self.input_size
+        th, tw = gh + (-gh % wh), gw + (-gw % ww)
+        return (th // wh) * (tw // ww), (th, tw) != (gh, gw)
+
+    def _dense_attention(self, qkv):
+        """Block._forward_attention of the reference, fused (window partition .. recombine)."""
+        b, n, _ = qkv.shape
+        dh = self.dim // self.heads
+        rel = self._rel_tables(qkv.dtype)
+        if self.window_size is not None:
+            n_win, padded = self._window_grid()
+            w2 = prod(self.window_size)
+            out = native.window_attention(qkv, self.heads, self.input_size, self.window_size,
+                                          pad_token=self.qkv.bias.detach(), rel=rel)
+            if self.count_mode:
+                if padded:
+                    self.qkv.counts["bias_flops"] += self.qkv.out_features  # forward_bias on the pad token
+                self.matmul.counts["matmul_flops"] += 2 * b * n_win * self.heads * w2 * w2 * dh
+                if rel is not None:
+                    self.relative_position.count_fused(b * n_win * self.heads, w2, w2)
+            return out
+        if n <= _SMALL_ATTENTION:
+            out = native.window_attention(qkv, self.heads, self.input_size, None, rel=rel)
+        else:
+            out = native.global_attention(qkv, self.heads, self.input_size, native.ATTN_DENSE, rel=rel)
+        if self.count_mode:
+            self.matmul.counts["matmul_flops"] += 2 * b * self.heads * n * n * dh
+            if rel is not None:
+                self.relative_position.count_fused(b * self.heads, n, n)
+        return out
+
+    def _mlp(self, c, out=None, idx=None):
+        h = self.mlp_1(c, act=native.ACT_GELU)
+        return self.mlp_2(h, out=out, idx=idx)
+
+    # Pair protocol: input is xa (+ xb), output is (branch, skip) whose sum is the block output.
+    def _forward_pair(self, xa, xb):
+        self._check_input(xa)
+        x = native.add(xa, xb) if xb is not None else xa
+        c = self._layer_norm_all(self.input_layer_norm, x)
+        attn = self._dense_attention(self.qkv(c))
+        x2 = native.add(self.projection(attn), x)
+        c2 = self._layer_norm_all(self.mlp_layer_norm, x2)
+        branch = self._mlp(c2)
+        self._count_adds(x)
+        return branch, x2
+
+
+class EventfulTokenwiseBlock(Block):
+    """Block with token gates / buffers around QKV, projection and MLP (reference blocks.py:399-463)."""
+
+    def __init__(self, gate_before_ln=False, stgt=False, **super_kwargs):
+        super().__init__(**super_kwargs)
+        self.gate_before_ln = gate_before_ln
+        self.stgt = stgt
+        token_gate_class = SimpleSTGTGate if stgt else TokenGate
+        self.qkv_gate = token_gate_class()
+        self.qkv_accumulator = TokenBuffer()
+        self.projection_gate = token_gate_class()
+        self.projection_accumulator = TokenBuffer()
+        self.mlp_gate = token_gate_class()
+        self.mlp_accumulator = TokenBuffer()
+
+    # ------------------------------------------------------------------ gate site
+    def _gate_site(self, gate, xa, xb, ln):
+        """
+        One gate site on an incremental frame.  Returns (x, c_tilde, index) where x = xa (+ xb) is the
+        site input (materialised only when there is a residual to add).
+        """
+        ln_p = None if ln is None else self._ln_params(ln)
+        pre, post = (None, ln_p) if self.gate_before_ln else (ln_p, None)
+        if gate.count_mode:
+            gate.counts["gate_flops"] += gate.p.numel()
+        spec = _policy_spec(gate.policy, xa.shape[-2])
+        if spec is not None:
+            if "threshold" in spec:
+                assert xa.shape[0] == 1  # policies.py:25
+            index, xsum = native.gate_select(xa, p=gate.p, xb=xb, want_sum=True, ln=pre, eps=LN_EPS, **spec)
+            x = xsum if xb is not None else xa
+        else:  # user-defined policy: materialise the error tensor and call it
+            x = native.add(xa, xb) if xb is not None else xa
+            c = x if pre is None else self._layer_norm_all(ln, x)
+            index = gate.policy(native.sub(c, gate.p), dim=-1)
+        index = index.contiguous()
+        gate.last_index = index  # selection trace (tests / visualisation); a reference, no copy
+        if post is not None:
+            c_tilde, _ = native.gate_gather(x, index, p=gate.p, ln=post, eps=LN_EPS, ln_after=True,
+                                            full_replace=self.stgt)
+        else:
+            c_tilde, _ = native.gate_gather(x, index, p=gate.p, ln=pre, eps=LN_EPS, full_replace=self.stgt)
+        return x, c_tilde, index
+
+    def _gate_first(self, gate, x, ln):
+        """Frame 0 of a gate site: returns the dense site output and initialises gate.p."""
+        gate.first = False
+        if ln is None:
+            gate.p = x
+            return x
+        c = self._layer_norm_all(ln, x)
+        gate.p = x.clone() if self.gate_before_ln else c
+        return c
+
+    @staticmethod
+    def _buffer_first(buffer, x):
+        buffer.first = False
+        buffer.b = x  # x is a fresh tensor owned by this block (the reference clones, modules.py:83)
+        return x
+
+    # ------------------------------------------------------------------ attention hooks
+    def _attention_first(self, qkv, index):
+        return self._dense_attention(qkv)
+
+    def _attention_incremental(self, qkv, index):
+        return self._dense_attention(qkv)
+
+    # ------------------------------------------------------------------ pair protocol
+    def forward(self, x):
+        branch, skip = self._forward_pair(x.contiguous(), None)
+        return native.add(branch, skip)
+
+    def _forward_pair(self, xa, xb):
+        self._check_input(xa)
+        if self.qkv_gate.first:
+            return self._first_pair(xa, xb)
+        n = xa.shape[-2]
+        # gate-accumulator 1: LN -> gate -> QKV -> buffer
+        x, c1, index = self._gate_site(self.qkv_gate, xa, xb, self.input_layer_norm)
+        qkv = self.qkv(c1, out=self.qkv_accumulator.b, idx=index)
+        attn = self._attention_incremental(qkv, index)
+        # gate-accumulator 2: gate -> projection -> buffer
+        _, c2, index2 = self._gate_site(self.projection_gate, attn, None, None)
+        proj = self.projection(c2, out=self.projection_accumulator.b, idx=index2)
+        # gate-accumulator 3: (+ skip) -> LN -> gate -> MLP -> buffer
+        x2, c3, index3 = self._gate_site(self.mlp_gate, proj, x, self.mlp_layer_norm)
+        branch = self._mlp(c3, out=self.mlp_accumulator.b, idx=index3)
+        self._count_adds(x2)
+        assert n == x2.shape[-2]
+        return branch, x2
+
+    def _first_pair(self, xa, xb):
+        x = native.add(xa, xb) if xb is not None else xa
+        c1 = self._gate_first(self.qkv_gate, x, self.input_layer_norm)
+        qkv = self._buffer_first(self.qkv_accumulator, self.qkv(c1))
+        attn = self._attention_first(qkv, None)
+        c2 = self._gate_first(self.projection_gate, attn, None)
+        proj = self._buffer_first(self.projection_accumulator, self.projection(c2))
+        x2 = native.add(proj, x)
+        c3 = self._gate_first(self.mlp_gate, x2, self.mlp_layer_norm)
+        branch = self._buffer_first(self.mlp_accumulator, self._mlp(c3))
+        self._count_adds(x2)
+        return branch, x2
+
+
+class EventfulMatmul1Block(EventfulTokenwiseBlock):
+    """
+    Adds eventfulness to the query-key product (reference blocks.py:466-540).  The reference keeps the
+    N x N product as state and refreshes k rows and k columns; since that state always equals
+    (q / scale) k^T of the current QKV buffer, this implementation recomputes the logits tile by tile
+    on tensor cores instead of storing them, so the attention here is the dense global kernel.
+    """
+
+    def __init__(self, **super_kwargs):
+        super().__init__(**super_kwargs)
+        assert self.window_size is None  # reference blocks.py:485
+        self.matmul_accumulator_1 = MatmulBuffer()
+
+    def _count_matmul_1(self, qkv, k_sel):
+        if self.count_mode:
+            b, n, _ = qkv.shape
+            dh = self.dim // self.heads
+            if k_sel is None:
+                self.matmul_accumulator_1.matmul.counts["matmul_flops"] += b * self.heads * n * n * dh
+            else:
+                self.matmul_accumulator_1.matmul.counts["matmul_flops"] += 2 * b * self.heads * n * k_sel * dh
+            if self.relative_position is not None:
+                self.relative_position.count_fused(b * self.heads, n, n)
+
+    def _global(self, qkv, mode, **kw):
+        return native.global_attention(qkv, self.heads, self.input_size, mode, rel=self._rel_tables(qkv.dtype), **kw)
+
+    def _attention_first(self, qkv, index):
+        self.matmul_accumulator_1.first = False
+        return self._attention_incremental(qkv, None)
+
+    def _attention_incremental(self, qkv, index):
+        b, n, _ = qkv.shape
+        self._count_matmul_1(qkv, None if index is None else index.shape[-1])
+        if self.count_mode:
+            self.matmul.counts["matmul_flops"] += b * self.heads * n * n * (self.dim // self.heads)
+        return self._global(qkv, native.ATTN_DENSE)
+
+
+class EventfulBlock(EventfulMatmul1Block):
+    """
+    Also gates the attention-value product (reference blocks.py:543-575): v-gate and A-gate forced by
+    the QKV gate's index, MatmulDeltaAccumulator update -- one fused kernel pair here.
+
+    State (allocated at frame 0, exposed with the reference's logical shapes):
+        v_gate.p                      (B, H, N, dh)  view of a (B, N, D) tensor
+        matmul_gate.p                 (B, H, N, N)   view of the column-major (B, H, N, NP) A-state
+        matmul_accumulator_2.product  (B, H, N, dh)  view of a (B, N, D) tensor
+    """
+
+    def __init__(self, **super_kwargs):
+        super().__init__(**super_kwargs)
+        self.v_gate = TokenDeltaGate()
+        self.matmul_gate = TokenDeltaGate(structure="col")
+        self.matmul_accumulator_2 = MatmulDeltaAccumulator()
+        self._a_state = self._v_state = self._acc = self._stats = None
+
+    def reset_self(self):
+        super().reset_self()
+        self._a_state = self._v_state = self._acc = self._stats = None
+
+    def _attention_first(self, qkv, index):
+        b, n, _ = qkv.shape
+        d, h = self.dim, self.heads
+        dh = d // h
+        n_pad = (n + 7) // 8 * 8
+        dev, dt = qkv.device, qkv.dtype
+        self._a_state = torch.zeros((b, h, n, n_pad), dtype=dt, device=dev)
+        self._v_state = torch.empty((b, n, d), dtype=dt, device=dev)
+        self._acc = torch.empty((b, n, d), dtype=dt, device=dev)
+        self._stats = torch.empty((b, h, n, 2), dtype=torch.float32, device=dev)
+        out = self._global(qkv, native.ATTN_FIRST, a_state=self._a_state, v_state=self._v_state, acc=self._acc,
+                           stats=self._stats)
+        self.matmul_accumulator_1.first = False
+        self.v_gate.first = self.matmul_gate.first = self.matmul_accumulator_2.first = False
+        self.v_gate.p = self._v_state.view(b, n, h, dh).permute(0, 2, 1, 3)
+        self.matmul_gate.p = self._a_state[..., :n].transpose(-1, -2)
+        self.matmul_accumulator_2.product = self._acc.view(b, n, h, dh).permute(0, 2, 1, 3)
+        self._count_matmul_1(qkv, None)
+        if self.count_mode:
+            self.matmul_accumulator_2.matmul.counts["matmul_flops"] += b * h * n * n * dh
+        return out
+
+    def _attention_incremental(self, qkv, index):
+        b, n, _ = qkv.shape
+        h = self.heads
+        dh = self.dim // h
+        k_sel = index.shape[-1]
+        self._count_matmul_1(qkv, k_sel)
+        if self.count_mode:
+            self.v_gate.counts["gate_flops"] += b * h * n * dh
+            self.matmul_gate.counts["gate_flops"] += b * h * n * n
+            self.matmul_accumulator_2.counts["accumulator_flops"] += b * (h * k_sel * dh + 2 * h * n * dh)
+            self.matmul_accumulator_2.matmul.counts["matmul_flops"] += 2 * b * h * n * k_sel * dh
+        return self._global(qkv, native.ATTN_DELTA, idx=index, a_state=self._a_state, v_state=self._v_state,
+                            acc=self._acc, stats=self._stats)

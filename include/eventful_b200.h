@@ -1,0 +1,166 @@
+/*
+ * eventful_b200.h -- C ABI of libeventful_b200.so, the sm_100a implementation of the
+ * gated sparse-token update path of Eventful Transformers.
+ *
+ * This is the drop-in boundary below the reference's Python module API
+ * (SURVEY.md 8(b)).  The reference has no FFI of its own (it is pure PyTorch);
+ * each entry point below names the reference call site(s) whose ATen dispatches
+ * it replaces.  All file:line citations are relative to the reference checkout.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors kept
+ *     alive by the Python layer); nothing is allocated or freed in the library;
+ *   - tensors are dense, row-major, 16-byte aligned; `dtype` is the element type
+ *     of every activation / state / weight pointer of the call;
+ *   - indices are int64 (torch.int64), shape (B, k);
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (they
+ *     are CUDA-graph capturable) and are thread-safe for distinct streams;
+ *   - return value 0 = ok, non-zero = error; et_last_error() (thread-local) says why.
+ *     There is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef EVENTFUL_B200_H
+#define EVENTFUL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { ET_F32 = 0, ET_BF16 = 1, ET_F16 = 2 } et_dtype;
+typedef enum { ET_SELECT_TOPK = 0, ET_SELECT_THRESHOLD = 1 } et_select_mode;
+typedef enum { ET_ACT_NONE = 0, ET_ACT_GELU = 1 } et_activation;          /* nn.GELU() exact erf, blocks.py:114 */
+typedef enum { ET_ATTN_DENSE = 0, ET_ATTN_FIRST = 1, ET_ATTN_DELTA = 2 } et_attn_mode;
+typedef enum { ET_OK = 0, ET_ERR_ARG = 1, ET_ERR_CUDA = 2, ET_ERR_UNSUPPORTED = 3 } et_status;
+
+/* ---- library / device queries ------------------------------------------------ */
+int         et_version(void);
+const char* et_last_error(void);
+/* Fails with ET_ERR_UNSUPPORTED unless the device is compute capability 10.x. */
+int         et_device_info(int device, int* cc_major, int* cc_minor, int* sm_count);
+
+/*
+ * Fused gate selection: [x = xa + xb] -> [c = LayerNorm(x)] -> e = c - p ->
+ * per-token L2 norm (fp32 accumulate, rounded to dtype) -> radix top-k or
+ * threshold selection, ONE launch.
+ * Replaces: CountedAdd (counting.py:16-19), nn.LayerNorm (blocks.py:442-444,458-460),
+ *   `c - self.p` (modules.py:149,196), TokenNormTopK.forward (policies.py:58-63),
+ *   TokenNormThreshold.forward (policies.py:20-32), TokenNormTopFraction (policies.py:88-95).
+ * Selection rule = torch CUDA radix select: strictly greater than the k-th value in
+ * ascending index order, then equal to it in ascending index order.
+ *   xa       (R, N, D)            gate input (or first addend)
+ *   xb       (R, N, D) or NULL    second addend (residual); sum rounded to dtype
+ *   xsum_out (R, N, D) or NULL    receives xa + xb
+ *   ln_w/b   (D) or NULL          LayerNorm affine, eps = ln_eps
+ *   p        (R, N, D) or NULL    gate reference state (NULL: the norm of c itself)
+ *   norm_out (R, N) float         per-token norms (value already rounded to dtype)
+ *   idx_out  (R, k) / (R, N)      selected indices; threshold mode writes count_out[r] of them
+ *   ticket   (R) int32            zero-initialised once; self-resetting
+ */
+int et_gate_select(const void* xa, const void* xb, void* xsum_out, const void* ln_w, const void* ln_b,
+                   float ln_eps, const void* p, int64_t R, int64_t N, int64_t D, int dtype, int mode,
+                   int64_t k, float threshold, float* norm_out, int64_t* idx_out, int32_t* count_out,
+                   int32_t* ticket, void* stream);
+
+/*
+ * Row gather + reference-state advance: c~ = c[idx], e~ = c[idx] - p[idx], p[idx] = c~.
+ * With LayerNorm parameters the gathered rows are normalised on the fly (ln_after = 0:
+ * LN precedes the gate, blocks.py:459-461; ln_after = 1: gate_before_ln, blocks.py:456-458,
+ * the state keeps the un-normalised rows).
+ * Replaces: c.gather / e.gather / p.scatter_ in TokenGate / TokenDeltaGate (modules.py:150-151,198-200).
+ *   count    (R) int32 or NULL   device-side number of valid indices per row (threshold policy)
+ *   full_replace != 0            SimpleSTGTGate: afterwards p <- c for every token (modules.py:44)
+ */
+int et_gate_gather(const void* x, const void* ln_w, const void* ln_b, float ln_eps, int ln_after, void* p,
+                   const int64_t* idx, const int32_t* count, int64_t R, int64_t N, int64_t D, int64_t k,
+                   int dtype, void* c_tilde, void* e_tilde, int full_replace, void* stream);
+
+/* Column-structure gate (structure="col", modules.py:161-163) on (R, N, M): gathers columns idx. */
+int et_gate_gather_cols(const void* c, void* p, const int64_t* idx, int64_t R, int64_t rows_per_index,
+                        int64_t N, int64_t M, int64_t k, int dtype, void* c_tilde, void* e_tilde, void* stream);
+
+/*
+ * TokenBuffer.forward_incremental (modules.py:86-97): buf[r, idx[r, j], :] = x[r, j, :]
+ * (structure 0 = "row") or buf[r, :, idx[r, j]] = x[r, :, j] (structure 1 = "col").
+ * `rows_per_index` lets one (B, k) index drive (B, H, ...) tensors (utils.py:198-211).
+ */
+int et_buffer_scatter(void* buf, const void* x, const int64_t* idx, const int32_t* count, int64_t R,
+                      int64_t rows_per_index, int64_t N, int64_t D, int64_t k, int dtype, int structure,
+                      void* stream);
+
+/* CountedAdd (counting.py:9-22): out = a + b elementwise (out may alias a). */
+int et_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+/* e = c - p (modules.py:149) for the generic (user-defined policy) gate path. */
+int et_sub(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+
+/* Test / tuning hook: key 1 forces the GEMM tile width BLOCK_N (0 = automatic). */
+int et_debug_set(int key, long long value);
+
+/*
+ * Gathered-row linear with scatter epilogue on tcgen05 tensor cores (TMA operand
+ * staging, TMEM accumulators):  y = act(A @ W^T + bias), then
+ *     out[(m / k) * n_out_rows + idx[m], :] = y[m, :]      (idx != NULL: TokenBuffer scatter)
+ *     out[m, :] = y[m, :]                                    (idx == NULL)
+ * Replaces: CountedLinear.forward (counting.py:157-162) at blocks.py:122,433,462 and
+ *   blocks.py:242-246 (mlp_1 + GELU + mlp_2), fused with TokenBuffer.scatter_ (modules.py:96).
+ *   A (M, K), W (n_feat, K) torch Linear layout (counting.py:142-143), bias (n_feat).
+ *   count (M / k) int32 or NULL: device-side valid rows per batch entry.
+ * dtype must be ET_BF16 or ET_F16 (fp32 accumulate).
+ */
+int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bias, int64_t n_feat, int act,
+              void* out, int64_t ld_out, const int64_t* idx, const int32_t* count, int64_t k,
+              int64_t n_out_rows, int dtype, void* stream);
+
+/*
+ * Dense windowed self-attention of EventfulTokenwiseBlock / Block, fused
+ * (window partition with qkv-bias pad tokens, head split, q/sqrt(dh) . k^T, decomposed
+ * rel-pos bias from the unscaled q, softmax, a . v, head merge, window recombine + crop).
+ * Replaces: Block._forward_attention and helpers (blocks.py:205-240,248-301,329-376),
+ *   RelativePositionEmbedding.forward (eventful_transformer/utils.py:139-171).
+ *   qkv (B, gh*gw + extra, 3*H*dh); pad_token (3*H*dh) = qkv.bias (blocks.py:275-287);
+ *   rel_y (wh, wh, dh), rel_x (ww, ww, dh) relative tables or NULL; out (B, N, H*dh).
+ *   window (wh, ww) = (0, 0) means one global window over all tokens (incl. class token).
+ */
+int et_window_attention(const void* qkv, const void* pad_token, const void* rel_y, const void* rel_x, void* out,
+                        void* workspace, int64_t B, int64_t N, int64_t gh, int64_t gw, int64_t wh, int64_t ww,
+                        int64_t heads, int64_t dh, int dtype, void* stream);
+
+/* Bytes of caller-provided scratch (`workspace`) the two attention entry points need:
+ * rel-pos bias tables (B, H, N, gh + gw) and, for the global DELTA mode, the v-gate deltas 2 x (B, k, H*dh).
+ * Pass wh = ww = 0 for global attention. */
+int64_t et_attn_workspace_bytes(int64_t B, int64_t N, int64_t gh, int64_t gw, int64_t wh, int64_t ww,
+                                int64_t heads, int64_t dh, int64_t k, int has_relpos);
+
+/*
+ * Global self-attention of the Eventful blocks over the QKV TokenBuffer.
+ *   mode DENSE : out = softmax(q k^T / sqrt(dh) + relpos) v                (Block / EventfulMatmul1Block)
+ *   mode FIRST : as DENSE, and initialises the gate / accumulator state (frame 0)
+ *   mode DELTA : A-gate + v-gate (forced by idx) + MatmulDeltaAccumulator update:
+ *        a_n = softmax(...)[:, idx];  dA = a_n - a_state[:, idx];  a_state[:, idx] = a_n
+ *        v_n = v[idx];  dV = v_n - v_state[idx];  v_state[idx] = v_n
+ *        acc += a_n . dV + dA . (v_n - dV);   out = acc
+ * Replaces: MatmulBuffer (modules.py:204-252; the product is recomputed, it always equals
+ *   (q/scale) k^T of the current buffer), softmax (blocks.py:522), TokenDeltaGate x2
+ *   (blocks.py:567-568, modules.py:187-201), MatmulDeltaAccumulator (modules.py:285-295),
+ *   RelativePositionEmbedding.forward(inplace=False) (blocks.py:521).
+ *   qkv (B, N, 3*H*dh); rel_y (gh, gh, dh) / rel_x (gw, gw, dh) or NULL (class-token models);
+ *   a_state (B, H, N, NP) stored COLUMN-major per head: a_state[b][h][col][row], row stride
+ *           NP = N rounded up to a multiple of 8 (16-byte segments of a selected column);
+ *   v_state (B, N, H*dh); acc (B, N, H*dh); out (B, N, H*dh); idx (B, k).
+ *   row_stats (B, H, N, 2) float workspace (row max, row sum).
+ */
+int et_global_attention(const void* qkv, const void* rel_y, const void* rel_x, int mode, const int64_t* idx,
+                        int64_t k, void* a_state, void* v_state, void* acc, void* out, float* row_stats,
+                        void* workspace, int64_t B, int64_t N, int64_t gh, int64_t gw, int64_t heads, int64_t dh,
+                        int dtype, void* stream);
+
+/* Generic strided batched matmul C = A @ B (fp32 accumulate) for the stand-alone
+ * MatmulBuffer / MatmulDeltaAccumulator modules (counting.py:165-175). Element strides. */
+int et_bmm(const void* A, const void* Bm, void* C, int64_t batch, int64_t M, int64_t N, int64_t K,
+           int64_t sab, int64_t sam, int64_t sak, int64_t sbb, int64_t sbk, int64_t sbn, int64_t scb,
+           int64_t scm, int64_t scn, int accumulate, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVENTFUL_B200_H */

@@ -1,0 +1,124 @@
+"""GPU parity of the attention kernels vs the oracle's restatement of blocks.py / modules.py (fp32 math on
+the same bf16-rounded inputs)."""
+import pytest
+import torch
+
+import eventful_oracle as orc
+from eventful_transformer import _native as native
+from eventful_transformer import blocks
+from gpu_util import DEV, one_block_oracle, rel_err
+
+pytestmark = pytest.mark.gpu
+DT = torch.bfloat16
+
+
+def block_params(dim, heads, rel, seed, std=0.5):
+    g = torch.Generator().manual_seed(seed)
+    p = {"blocks.0.qkv.bias": (0.5 * torch.randn(3 * dim, generator=g)).to(DT).float()}
+    if rel is not None:
+        p["blocks.0.relative_position.y_embedding"] = (std * torch.randn(2 * rel[0] - 1, dim // heads, generator=g)).to(DT).float()
+        p["blocks.0.relative_position.x_embedding"] = (std * torch.randn(2 * rel[1] - 1, dim // heads, generator=g)).to(DT).float()
+    return p
+
+
+def gpu_block(cls, dim, heads, input_size, params, rel=None, window=None):
+    kw = dict(dim=dim, heads=heads, input_size=input_size, mlp_ratio=4, window_size=window)
+    if rel is not None:
+        kw["relative_embedding_size"] = rel
+    blk = getattr(blocks, cls)(**kw)
+    sd = {k.replace("blocks.0.", ""): v for k, v in params.items()}
+    blk.load_state_dict(sd, strict=False)
+    return blk.to(DEV).to(DT).eval()
+
+
+WINDOW_CASES = [  # dim, heads, grid, window, rel size, batch
+    (768, 12, (16, 16), (14, 14), (64, 64), 2),   # ViTDet-B windowed block with padding 16 -> 28
+    (768, 12, (28, 28), (14, 14), (64, 64), 1),   # no padding
+    (32, 2, (7, 7), (4, 4), (5, 5), 3),           # dh = 16, padding 7 -> 8
+    (64, 2, (9, 5), (3, 5), (4, 4), 2),           # dh = 32, rectangular
+]
+
+
+@pytest.mark.parametrize("dim,heads,grid,window,rel,batch", WINDOW_CASES)
+def test_window_attention(dim, heads, grid, window, rel, batch):
+    params = block_params(dim, heads, rel, seed=dim + grid[0])
+    n = grid[0] * grid[1]
+    qkv = torch.randn(batch, n, 3 * dim, generator=torch.Generator().manual_seed(1)).to(DT)
+    oracle = one_block_oracle(params, dim, heads, grid, orc.TOKENWISE, window=window, rel=rel)
+    want = oracle._attention_dense(0, qkv.float())
+    blk = gpu_block("EventfulTokenwiseBlock", dim, heads, grid, params, rel=rel, window=window)
+    got = blk._dense_attention(qkv.to(DEV))
+    assert got.shape == want.shape
+    assert rel_err(got.cpu(), want) < 2e-2
+
+
+@pytest.mark.parametrize("dim,heads,grid,rel,cls_token", [(768, 12, (14, 14), None, True), (32, 2, (7, 7), (5, 5), False),
+                                                         (768, 12, (20, 20), None, True), (64, 4, (12, 12), (12, 12), False)])
+def test_small_dense_attention(dim, heads, grid, rel, cls_token):
+    params = block_params(dim, heads, rel, seed=5)
+    n = grid[0] * grid[1] + int(cls_token)
+    qkv = torch.randn(2, n, 3 * dim, generator=torch.Generator().manual_seed(2)).to(DT)
+    oracle = one_block_oracle(params, dim, heads, grid, orc.DENSE, rel=rel, has_class_token=cls_token)
+    want = oracle._attention_dense(0, qkv.float())
+    blk = gpu_block("Block", dim, heads, grid, params, rel=rel)
+    assert rel_err(blk._dense_attention(qkv.to(DEV)).cpu(), want) < 2e-2
+
+
+GLOBAL_CASES = [  # dim, heads, grid, rel, extra tokens, k, batch
+    (768, 12, (32, 32), (64, 64), 0, 300, 1),     # interpolated rel tables, ragged k
+    (768, 12, (14, 14), None, 1, 64, 3),          # ViViT shape: 197 tokens incl. class token, batch of views
+    (32, 2, (7, 7), (5, 5), 0, 12, 2),            # dh = 16, N not a multiple of 8
+    (128, 2, (24, 24), (24, 24), 0, 576, 1),      # k == N (refresh everything)
+]
+
+
+@pytest.mark.parametrize("dim,heads,grid,rel,extra,k,batch", GLOBAL_CASES)
+def test_global_eventful_attention_sequence(dim, heads, grid, rel, extra, k, batch):
+    """FIRST then DELTA frames vs the oracle's matmul_buffer + gates + delta_accumulator; also checks the state."""
+    params = block_params(dim, heads, rel, seed=9)
+    n = grid[0] * grid[1] + extra
+    g = torch.Generator().manual_seed(3)
+    oracle = one_block_oracle(params, dim, heads, grid, orc.EVENTFUL, rel=rel, has_class_token=bool(extra))
+    blk = gpu_block("EventfulBlock", dim, heads, grid, params, rel=rel)
+    qkv = torch.randn(batch, n, 3 * dim, generator=g).to(DT)
+    buf_cpu, buf_gpu = qkv.float().clone(), qkv.to(DEV).clone()
+    want = oracle._attention_eventful(0, buf_cpu, None)
+    got = blk._attention_first(buf_gpu, None)
+    assert rel_err(got.cpu(), want) < 2e-2
+    for t in range(1, 4):
+        idx = torch.stack([torch.randperm(n, generator=g)[:k] for _ in range(batch)])
+        rows = (qkv.float().gather(1, idx.unsqueeze(-1).expand(-1, -1, 3 * dim))
+                + 0.5 * torch.randn(batch, k, 3 * dim, generator=g)).to(DT)
+        buf_cpu.scatter_(1, idx.unsqueeze(-1).expand(-1, -1, 3 * dim), rows.float())
+        buf_gpu.scatter_(1, idx.to(DEV).unsqueeze(-1).expand(-1, -1, 3 * dim), rows.to(DEV))
+        want = oracle._attention_eventful(0, buf_cpu, idx)
+        got = blk._attention_incremental(buf_gpu, idx.to(DEV))
+        assert rel_err(got.cpu(), want) < 3e-2, t
+        # state parity: A-gate reference (logical (B, H, N, N)), v-gate reference, accumulator
+        st = oracle.state[0]
+        assert rel_err(blk.matmul_gate.p.cpu(), st["matmul_gate"]["p"]) < 2e-2
+        assert torch.equal(blk.v_gate.p.cpu().float(), st["v_gate"]["p"])
+        assert rel_err(blk.matmul_accumulator_2.product.cpu(), st["matmul_accumulator_2"]["product"]) < 3e-2
+
+
+def test_global_dense_attention_large():
+    dim, heads, grid, rel = 768, 12, (32, 32), (64, 64)
+    params = block_params(dim, heads, rel, seed=11)
+    qkv = torch.randn(1, 1024, 3 * dim, generator=torch.Generator().manual_seed(4)).to(DT)
+    oracle = one_block_oracle(params, dim, heads, grid, orc.DENSE, rel=rel)
+    want = oracle._attention_dense(0, qkv.float())
+    blk = gpu_block("EventfulMatmul1Block", dim, heads, grid, params, rel=rel)
+    got = blk._attention_incremental(qkv.to(DEV), None)
+    assert rel_err(got.cpu(), want) < 2e-2
+
+
+def test_delta_with_static_input_is_exactly_stationary():
+    """Identical frames: a_n == p bit-for-bit, dV == 0, so the accumulator must not move at all."""
+    dim, heads, grid = 768, 12, (16, 16)
+    params = block_params(dim, heads, (64, 64), seed=13)
+    blk = gpu_block("EventfulBlock", dim, heads, grid, params, rel=(64, 64))
+    qkv = torch.randn(1, 256, 3 * dim, generator=torch.Generator().manual_seed(5)).to(DT).to(DEV)
+    first = blk._attention_first(qkv, None).clone()
+    idx = torch.randperm(256, generator=torch.Generator().manual_seed(6))[:100].view(1, -1).to(DEV)
+    again = blk._attention_incremental(qkv, idx)
+    assert torch.equal(first, again)

@@ -1,0 +1,83 @@
+"""GPU parity of et_linear (tcgen05 GEMM + bias/GELU + TokenBuffer scatter epilogue) vs fp32 torch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from eventful_transformer import _native as native
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+SHAPES = [  # (M, K, n_feat)
+    (2048, 768, 2304), (2048, 768, 768), (2048, 768, 3072), (2048, 3072, 768),  # ViTDet-B, k = 2048
+    (512, 768, 2304), (768, 768, 3072), (4096, 768, 768),
+    (100, 32, 96), (257, 72, 136), (1, 768, 768), (129, 64, 8), (300, 40, 264),  # ragged M / K / n tails
+]
+
+
+def reference(x, w, b, act):
+    y = x.float() @ w.float().t() + (0 if b is None else b.float())
+    return F.gelu(y) if act else y
+
+
+def make(m, k, f, dtype, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(m, k, generator=g).to(dtype).to(DEV)
+    w = (torch.randn(f, k, generator=g) / k ** 0.5).to(dtype).to(DEV)
+    b = torch.randn(f, generator=g).to(dtype).to(DEV)
+    return x, w, b
+
+
+def check(y, ref, dtype):
+    tol = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    err = (y.float() - ref).abs()
+    bound = tol * ref.abs() + tol * float(ref.abs().mean())
+    assert bool((err <= bound).all()), f"max err {float(err.max())} (ref scale {float(ref.abs().mean())})"
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,k,f", SHAPES)
+@pytest.mark.parametrize("act", [0, 1])
+def test_linear_dense(m, k, f, act, dtype):
+    x, w, b = make(m, k, f, dtype)
+    y = native.linear(x, w, b, act=act)
+    assert y.shape == (m, f) and y.dtype == dtype
+    check(y, reference(x, w, b, act), dtype)
+
+
+@pytest.mark.parametrize("block_n", [64, 96, 128, 192, 256])
+def test_linear_every_tile_width(block_n):
+    try:
+        native.lib().et_debug_set(1, block_n)
+        for m, k, f in [(2048, 768, 2304), (257, 72, 136), (640, 3072, 768)]:
+            x, w, b = make(m, k, f, torch.bfloat16, seed=block_n)
+            check(native.linear(x, w, b), reference(x, w, b, 0), torch.bfloat16)
+            check(native.linear(x, w, None, act=1), reference(x, w, None, 1), torch.bfloat16)
+    finally:
+        native.lib().et_debug_set(1, 0)
+
+
+@pytest.mark.parametrize("batch,n,k_sel,kdim,f", [(1, 4096, 2048, 768, 2304), (3, 197, 64, 768, 768), (2, 50, 7, 32, 96)])
+def test_linear_scatter_epilogue(batch, n, k_sel, kdim, f):
+    """out[b, idx[b, j]] = y[b, j]; untouched rows keep their previous content (TokenBuffer semantics)."""
+    dtype = torch.bfloat16
+    x, w, b = make(batch * k_sel, kdim, f, dtype, seed=3)
+    g = torch.Generator().manual_seed(4)
+    idx = torch.stack([torch.randperm(n, generator=g)[:k_sel] for _ in range(batch)]).to(DEV)
+    buf = torch.full((batch, n, f), 7.0, dtype=dtype, device=DEV)
+    out = native.linear(x.view(batch, k_sel, kdim), w, b, out=buf, idx=idx)
+    assert out.data_ptr() == buf.data_ptr()
+    dense = native.linear(x, w, b).view(batch, k_sel, f)
+    want = torch.full((batch, n, f), 7.0, dtype=dtype, device=DEV)
+    want.scatter_(1, idx.unsqueeze(-1).expand(-1, -1, f), dense)
+    assert torch.equal(buf, want)
+    check(dense.view(-1, f), reference(x, w, b, 0), dtype)
+
+
+def test_linear_rejects_fp32_and_bad_shapes():
+    x = torch.zeros(8, 64, device=DEV)
+    with pytest.raises(native.NativeError, match="bf16/fp16"):
+        native.linear(x, torch.zeros(16, 64, device=DEV), None)
+    with pytest.raises(native.NativeError, match="multiples of 8"):
+        native.linear(torch.zeros(8, 12, device=DEV, dtype=torch.bfloat16),
+                      torch.zeros(16, 12, device=DEV, dtype=torch.bfloat16), None)
