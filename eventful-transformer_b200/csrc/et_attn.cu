@@ -674,6 +674,9 @@ int set_smem(K kernel, int bytes) {
     return ET_OK;
 }
 
+// every sub-buffer of the workspace starts on a 16-byte boundary (element counts rounded up to 8)
+inline size_t align8(size_t n) { return (n + 7) / 8 * 8; }
+
 // Bias tables and the v-gate deltas live in a CALLER-PROVIDED workspace (et_attn_workspace_bytes);
 // the library never allocates.
 template <typename T, int DH>
@@ -683,12 +686,13 @@ int run_window(const AttnArgs& a, const void* rel_y, const void* rel_x, void* bi
     AttnArgs args = a;
     if (rel_y != nullptr) {
         T* bh = static_cast<T*>(bias_ws);
-        T* bw = bh + (size_t)a.B * nwin * a.H * a.Wn * lh;
+        T* bw = bh + align8((size_t)a.B * nwin * a.H * a.Wn * lh);
         const int smem = ((lh > lw ? lh : lw) * 2) * (DH + 1) * (int)sizeof(float);
         int rc = set_smem(relpos_bias_kernel<T, DH>, smem);
         if (rc) return rc;
         relpos_bias_kernel<T, DH><<<dim3(lh + lw, a.H, a.B * nwin), 128, smem, s>>>(
             a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw);
+        ET_COUNT_LAUNCH(1);
         args.bias_h = bh;
         args.bias_w = bw;
     }
@@ -696,6 +700,7 @@ int run_window(const AttnArgs& a, const void* rel_y, const void* rel_x, void* bi
     int rc = set_smem(window_attention_kernel<T, DH>, smem);
     if (rc) return rc;
     window_attention_kernel<T, DH><<<dim3((a.Wn + BQ - 1) / BQ, a.H, a.B * nwin), kAttnThreads, smem, s>>>(args);
+    ET_COUNT_LAUNCH(1);
     return ET_OK;
 }
 
@@ -705,15 +710,16 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     const int D = a.H * DH;
     // workspace layout: [bias_h | bias_w | dV | Vd]
     T* bh = static_cast<T*>(ws);
-    T* bw = bh + (rel_y ? (size_t)a.B * a.H * a.N * a.gh : 0);
-    T* dV = bw + (rel_y ? (size_t)a.B * a.H * a.N * a.gw : 0);
-    T* Vd = dV + (size_t)a.B * a.k * D;
+    T* bw = bh + (rel_y ? align8((size_t)a.B * a.H * a.N * a.gh) : 0);
+    T* dV = bw + (rel_y ? align8((size_t)a.B * a.H * a.N * a.gw) : 0);
+    T* Vd = dV + align8((size_t)a.B * a.k * D);
     if (rel_y != nullptr) {
         const int smem = ((a.gh > a.gw ? a.gh : a.gw) * 2) * (DH + 1) * (int)sizeof(float);
         int rc = set_smem(relpos_bias_kernel<T, DH>, smem);
         if (rc) return rc;
         relpos_bias_kernel<T, DH><<<dim3(a.gh + a.gw, a.H, a.B), 128, smem, s>>>(
             a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw);
+        ET_COUNT_LAUNCH(1);
         args.bias_h = bh;
         args.bias_w = bw;
     }
@@ -723,28 +729,34 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
         if (total > 0)
             vgate_kernel<T><<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, static_cast<T*>(v_state), a.idx, dV, Vd, a.N, D,
                                                                       a.k, total);
+        ET_COUNT_LAUNCH(1);
         args.dV = dV;
         args.Vd = Vd;
     } else if (a.mode == ET_ATTN_FIRST) {
         const long long total = (long long)a.B * a.N * (D / 8);
         vgate_kernel<T><<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, static_cast<T*>(v_state), nullptr, nullptr, nullptr,
                                                                   a.N, D, a.N, total);
+        ET_COUNT_LAUNCH(1);
     }
     const dim3 grid((a.N + BQ - 1) / BQ, a.H, a.B);
     const int smem_a = (BQ * (DH + 8) + BKV * (DH + 8) + BQ * (a.gh + 1 + a.gw + 1)) * (int)sizeof(T) + 16;
     int rc = set_smem(attn_stats_kernel<T, DH>, smem_a);
     if (rc) return rc;
     attn_stats_kernel<T, DH><<<grid, kAttnThreads, smem_a, s>>>(args);
+    ET_COUNT_LAUNCH(1);
     const int smem_b = apply_smem<T, DH>(a.gh, a.gw);
     if (a.mode == ET_ATTN_DELTA) {
         if ((rc = set_smem(attn_apply_kernel<T, DH, ET_ATTN_DELTA>, smem_b))) return rc;
         if (a.k > 0) attn_apply_kernel<T, DH, ET_ATTN_DELTA><<<grid, kAttnThreads, smem_b, s>>>(args);
+        ET_COUNT_LAUNCH(1);
     } else if (a.mode == ET_ATTN_FIRST) {
         if ((rc = set_smem(attn_apply_kernel<T, DH, ET_ATTN_FIRST>, smem_b))) return rc;
         attn_apply_kernel<T, DH, ET_ATTN_FIRST><<<grid, kAttnThreads, smem_b, s>>>(args);
+        ET_COUNT_LAUNCH(1);
     } else {
         if ((rc = set_smem(attn_apply_kernel<T, DH, ET_ATTN_DENSE>, smem_b))) return rc;
         attn_apply_kernel<T, DH, ET_ATTN_DENSE><<<grid, kAttnThreads, smem_b, s>>>(args);
+        ET_COUNT_LAUNCH(1);
     }
     return ET_OK;
 }
@@ -767,10 +779,10 @@ int64_t et_attn_workspace_bytes(int64_t B, int64_t N, int64_t gh, int64_t gw, in
     int64_t elems = 0;
     if (wh > 0) {
         const int64_t nw = ((gh + wh - 1) / wh) * ((gw + ww - 1) / ww);
-        if (has_relpos) elems += B * nw * heads * wh * ww * (wh + ww);
+        if (has_relpos) elems += align8(B * nw * heads * wh * ww * wh) + align8(B * nw * heads * wh * ww * ww);
     } else {
-        if (has_relpos) elems += B * heads * N * (gh + gw);
-        elems += 2 * B * k * heads * dh;
+        if (has_relpos) elems += align8(B * heads * N * gh) + align8(B * heads * N * gw);
+        elems += 2 * align8(B * k * heads * dh);
     }
     return elems * 2 + 256;
 }

@@ -123,3 +123,7 @@ __device__ __forceinline__ float group_sum(float v) {
     }
 
 static inline cudaStream_t et_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Number of kernels this library has enqueued (bench.py reports it as gpu_launches).
+extern long long g_et_launches;
+#define ET_COUNT_LAUNCH(n) (g_et_launches += (n))

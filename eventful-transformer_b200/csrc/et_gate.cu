@@ -10,6 +10,7 @@
 #include "et_common.cuh"
 
 thread_local char g_et_error[512] = "";
+long long g_et_launches = 0;
 
 namespace {
 
@@ -486,6 +487,7 @@ template <typename T, int LPT, int CPL>
 struct SelectLauncher {
     static int run(const GateArgs& a, int ctas_per_row, int R, cudaStream_t s) {
         gate_select_kernel<T, LPT, CPL><<<dim3(ctas_per_row, R), kGateThreads, 0, s>>>(a);
+        ET_COUNT_LAUNCH(1);
         return 0;
     }
 };
@@ -494,6 +496,7 @@ struct GatherLauncher {
     static int run(const GatherArgs& a, cudaStream_t s) {
         constexpr int GROUPS = kGateThreads / LPT;
         gate_gather_kernel<T, LPT, CPL><<<(a.total_rows + GROUPS - 1) / GROUPS, kGateThreads, 0, s>>>(a);
+        ET_COUNT_LAUNCH(1);
         return 0;
     }
 };
@@ -502,6 +505,7 @@ struct ReplaceLauncher {
     static int run(const GatherArgs& a, cudaStream_t s) {
         constexpr int GROUPS = kGateThreads / LPT;
         gate_replace_kernel<T, LPT, CPL><<<(a.total_rows + GROUPS - 1) / GROUPS, kGateThreads, 0, s>>>(a);
+        ET_COUNT_LAUNCH(1);
         return 0;
     }
 };
@@ -518,6 +522,8 @@ int grid_for(long long work_items, int threads) {
 extern "C" {
 
 int et_version(void) { return 100; }
+
+long long et_launch_count(void) { return g_et_launches; }
 
 const char* et_last_error(void) { return g_et_error; }
 
@@ -620,6 +626,7 @@ int et_gate_gather_cols(const void* c, void* p, const int64_t* idx, int64_t R, i
             static_cast<const T*>(c), static_cast<T*>(p), reinterpret_cast<const long long*>(idx), (int)rows_per_index,
             (int)N, (int)M, (int)k, static_cast<T*>(c_tilde), static_cast<T*>(e_tilde), total);
     });
+    ET_COUNT_LAUNCH(1);
     ET_CHECK_LAUNCH("et_gate_gather_cols");
     return ET_OK;
 }
@@ -647,6 +654,7 @@ int et_buffer_scatter(void* buf, const void* x, const int64_t* idx, const int32_
                 (int)rows_per_index, (int)N, (int)D, (int)k, total);
         }
     });
+    ET_COUNT_LAUNCH(1);
     ET_CHECK_LAUNCH("et_buffer_scatter");
     return ET_OK;
 }
@@ -671,6 +679,7 @@ static int add_impl(const void* a, const void* b, void* out, int64_t n, int dtyp
         add_kernel<T><<<grid_for(n / VEC, 256), 256, 0, et_stream(stream)>>>(
             static_cast<const T*>(a), static_cast<const T*>(b), static_cast<T*>(out), n / VEC, sign);
     });
+    ET_COUNT_LAUNCH(1);
     ET_CHECK_LAUNCH("et_add");
     return ET_OK;
 }

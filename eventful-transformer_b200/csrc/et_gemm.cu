@@ -312,6 +312,7 @@ int launch_linear(const void* A, const void* W, const LinearArgs& args, cudaStre
     if (rc) return rc;
     dim3 grid((args.n_feat + BLOCK_N - 1) / BLOCK_N, (args.M + BLOCK_M - 1) / BLOCK_M);
     linear_tcgen05_kernel<BLOCK_N, STAGES><<<grid, kGemmThreads, L::TOTAL, stream>>>(ta, tw, args);
+    ET_COUNT_LAUNCH(1);
     return ET_OK;
 }
 

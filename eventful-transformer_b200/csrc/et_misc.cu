@@ -58,6 +58,7 @@ extern "C" int et_bmm(const void* A, const void* Bm, void* C, int64_t batch, int
     const dim3 grid((unsigned)((N + TILE - 1) / TILE), (unsigned)((M + TILE - 1) / TILE), (unsigned)batch);
     ET_CHECK_ARG(grid.y <= 65535, "et_bmm: M too large");
     ET_DISPATCH_DTYPE(dtype, T, { bmm_kernel<T><<<grid, TILE * TILE, 0, et_stream(stream)>>>(a); });
+    ET_COUNT_LAUNCH(1);
     ET_CHECK_LAUNCH("et_bmm");
     return ET_OK;
 }

@@ -26,6 +26,7 @@ _DTYPES = {torch.float32: ET_F32, torch.bfloat16: ET_BF16, torch.float16: ET_F16
 
 _SIGNATURES = {
     "et_version": (c_int, []),
+    "et_launch_count": (c_longlong, []),
     "et_last_error": (ctypes.c_char_p, []),
     "et_device_info": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "et_gate_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64,

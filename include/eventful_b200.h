@@ -35,6 +35,8 @@ typedef enum { ET_OK = 0, ET_ERR_ARG = 1, ET_ERR_CUDA = 2, ET_ERR_UNSUPPORTED = 
 
 /* ---- library / device queries ------------------------------------------------ */
 int         et_version(void);
+/* Kernels enqueued by this library so far in this process (bench.py reports the per-run delta as gpu_launches). */
+long long   et_launch_count(void);
 const char* et_last_error(void);
 /* Fails with ET_ERR_UNSUPPORTED unless the device is compute capability 10.x. */
 int         et_device_info(int device, int* cc_major, int* cc_minor, int* sm_count);

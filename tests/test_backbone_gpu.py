@@ -51,7 +51,7 @@ def test_backbone_matches_oracle_given_identical_index_sets(name):
             if not forced_ok and t > 0:
                 bound = 0.15  # free-running selections may diverge (the method is lossy)
             assert err <= bound, f"{name} frame {t}: rel err {err:.4f} > {bound:.4f} (reference bf16 err {ref_err})"
-            if forced is not None and t > 0 and case["policy"][0] != "threshold":
+            if forced is not None and t > 0 and case["policy"] is not None and case["policy"][0] != "threshold":
                 # the CUDA selection and the oracle's free selection on its own (near-identical) inputs agree
                 exact_free = {key: idx for key, idx in exact.trace}
                 assert set(exact_free) == set(forced)
