@@ -175,10 +175,14 @@ __device__ __forceinline__ void add_bias(float (&s)[8][4], const T* bh, const T*
 
 // ---------------------------------------------------------------- rel-pos bias tables
 // grid (wh + ww, H, B * n_windows); y-lines compute bias_h, x-lines compute bias_w.
+// One line = all tokens sharing a query coordinate, so they share one (coords x DH) relative table:
+// bias[token][coord] = q[token] . table[coord]  -> a small tensor-core GEMM per line (mma.sync m16n8k16).
 template <typename T, int DH>
-__global__ void __launch_bounds__(128) relpos_bias_kernel(const AttnArgs a, const T* rel_y, const T* rel_x, T* bias_h,
-                                                           T* bias_w) {
-    extern __shared__ float sm[];
+__global__ void __launch_bounds__(kAttnThreads) relpos_bias_kernel(const AttnArgs a, const T* rel_y, const T* rel_x,
+                                                                    T* bias_h, T* bias_w) {
+    constexpr int LD = DH + 8;
+    __shared__ __align__(16) T Qs[BQ * LD];
+    __shared__ __align__(16) T Ts[BKV * LD];
     const TokenMap map = make_map(a);
     const int line = blockIdx.x, h = blockIdx.y, bw = blockIdx.z;
     const int nwin = a.windowed ? a.nwx * a.nwy : 1;
@@ -189,27 +193,42 @@ __global__ void __launch_bounds__(128) relpos_bias_kernel(const AttnArgs a, cons
     const int ntok = ymode ? lw : lh;                // tokens on this line
     const int nout = ymode ? lh : lw;                // key coordinates
     const T* table = (ymode ? rel_y + (size_t)fixed * lh * DH : rel_x + (size_t)fixed * lw * DH);
-    float* tab = sm;                                 // [nout][DH + 1]
-    float* qs = sm + nout * (DH + 1);                // [ntok][DH + 1]
     const int D = a.H * DH;
-    for (int i = threadIdx.x; i < nout * DH; i += blockDim.x) tab[(i / DH) * (DH + 1) + i % DH] = ldf(table + i);
-    for (int i = threadIdx.x; i < ntok * DH; i += blockDim.x) {
-        const int j = i / DH, c = i - j * DH;
-        const int t = ymode ? fixed * lw + j : j * lw + fixed;
-        const int tok = map.token(win, t);
-        const T* src = tok >= 0 ? static_cast<const T*>(a.qkv) + ((size_t)b * a.N + tok) * 3 * D + h * DH
-                                : static_cast<const T*>(a.pad_token) + h * DH;
-        qs[j * (DH + 1) + c] = ldf(src + c);
-    }
-    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tq = lane & 3;
     T* dst = ymode ? bias_h : bias_w;
-    for (int o = threadIdx.x; o < ntok * nout; o += blockDim.x) {
-        const int j = o / nout, kc = o - j * nout;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < DH; ++c) acc = fmaf(qs[j * (DH + 1) + c], tab[kc * (DH + 1) + c], acc);
-        const int t = ymode ? fixed * lw + j : j * lw + fixed;
-        dst[(((size_t)bw * a.H + h) * a.Wn + t) * nout + kc] = ElemTraits<T>::from_float(acc);
+    for (int tok0 = 0; tok0 < ntok; tok0 += BQ) {
+        __syncthreads();
+        stage_rows<T, DH, LD>(Qs, BQ, [&](int r) -> const T* {
+            const int j = tok0 + r;
+            if (j >= ntok) return nullptr;
+            const int tok = map.token(win, ymode ? fixed * lw + j : j * lw + fixed);
+            return tok >= 0 ? static_cast<const T*>(a.qkv) + ((size_t)b * a.N + tok) * 3 * D + h * DH
+                            : static_cast<const T*>(a.pad_token) + h * DH;
+        });
+        for (int out0 = 0; out0 < nout; out0 += BKV) {
+            __syncthreads();
+            stage_rows<T, DH, LD>(Ts, BKV, [&](int r) -> const T* {
+                return out0 + r < nout ? table + (size_t)(out0 + r) * DH : nullptr;
+            });
+            cp_async_wait_all();
+            __syncthreads();
+            uint32_t qf[DH / 16][4];
+            load_q_frags<T, DH, LD>(qf, Qs, warp, lane);
+            float s[8][4];
+            qk_tile<T, DH, LD>(s, qf, Ts, lane);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = tok0 + warp * 16 + g + (i >> 1) * 8;
+                    const int kc = out0 + nt * 8 + tq * 2 + (i & 1);
+                    if (j < ntok && kc < nout) {
+                        const int t = ymode ? fixed * lw + j : j * lw + fixed;
+                        dst[(((size_t)bw * a.H + h) * a.Wn + t) * nout + kc] = ElemTraits<T>::from_float(s[nt][i]);
+                    }
+                }
+        }
     }
 }
 
@@ -687,10 +706,7 @@ int run_window(const AttnArgs& a, const void* rel_y, const void* rel_x, void* bi
     if (rel_y != nullptr) {
         T* bh = static_cast<T*>(bias_ws);
         T* bw = bh + align8((size_t)a.B * nwin * a.H * a.Wn * lh);
-        const int smem = ((lh > lw ? lh : lw) * 2) * (DH + 1) * (int)sizeof(float);
-        int rc = set_smem(relpos_bias_kernel<T, DH>, smem);
-        if (rc) return rc;
-        relpos_bias_kernel<T, DH><<<dim3(lh + lw, a.H, a.B * nwin), 128, smem, s>>>(
+        relpos_bias_kernel<T, DH><<<dim3(lh + lw, a.H, a.B * nwin), kAttnThreads, 0, s>>>(
             a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw);
         ET_COUNT_LAUNCH(1);
         args.bias_h = bh;
@@ -714,10 +730,7 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     T* dV = bw + (rel_y ? align8((size_t)a.B * a.H * a.N * a.gw) : 0);
     T* Vd = dV + align8((size_t)a.B * a.k * D);
     if (rel_y != nullptr) {
-        const int smem = ((a.gh > a.gw ? a.gh : a.gw) * 2) * (DH + 1) * (int)sizeof(float);
-        int rc = set_smem(relpos_bias_kernel<T, DH>, smem);
-        if (rc) return rc;
-        relpos_bias_kernel<T, DH><<<dim3(a.gh + a.gw, a.H, a.B), 128, smem, s>>>(
+        relpos_bias_kernel<T, DH><<<dim3(a.gh + a.gw, a.H, a.B), kAttnThreads, 0, s>>>(
             a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw);
         ET_COUNT_LAUNCH(1);
         args.bias_h = bh;

@@ -108,7 +108,7 @@ __device__ __forceinline__ void layer_norm_row(float (&v)[CPL * ElemTraits<T>::V
 // ------------------------------------------------------------------------------------------
 // Selection stage, executed by one CTA per row after all norms of the row are visible.
 // ------------------------------------------------------------------------------------------
-__device__ void select_row(const GateArgs& a, int r, uint32_t* s_keys, int* s_hist, int* s_misc) {
+__device__ void select_row(const GateArgs& a, int r, uint32_t* s_keys, int* s_hist, int* s_whist, int* s_misc) {
     const int tid = threadIdx.x;
     const int N = a.N;
     const float* norm = a.norm + (size_t)r * N;
@@ -148,11 +148,29 @@ __device__ void select_row(const GateArgs& a, int r, uint32_t* s_keys, int* s_hi
     int remaining = a.k;
     for (int pass = 0; pass < a.passes; ++pass) {
         const int shift = 24 - 8 * pass;
-        s_hist[tid] = 0;
+        // per-warp histograms with warp-aggregated increments: norms cluster in a handful of digit bins,
+        // so plain shared atomics would serialise the whole CTA on one bank
+#pragma unroll
+        for (int w = 0; w < kGateThreads / 32; ++w) s_whist[w * 256 + tid] = 0;
         __syncthreads();
-        for (int i = tid; i < N; i += kGateThreads) {
-            const uint32_t key = key_at(i);
-            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xffu], 1);
+        for (int base = 0; base < N; base += kGateThreads) {
+            const int i = base + tid;
+            const uint32_t key = i < N ? key_at(i) : 0u;
+            const bool on = i < N && (key & mask) == prefix;
+            const unsigned active = __ballot_sync(0xffffffffu, on);
+            if (on) {
+                const uint32_t bin = (key >> shift) & 0xffu;
+                const unsigned peers = __match_any_sync(active, bin);
+                if (lane == __ffs(peers) - 1) s_whist[warp * 256 + bin] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        {
+            int total = 0;
+#pragma unroll
+            for (int w = 0; w < kGateThreads / 32; ++w) total += s_whist[w * 256 + tid];
+            s_hist[tid] = total;
         }
         __syncthreads();
         if (warp == 0) {
@@ -231,6 +249,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
     constexpr int GROUPS = kGateThreads / LPT;
     __shared__ uint32_t s_keys[kSmemKeys];
     __shared__ int s_hist[256];
+    __shared__ int s_whist[(kGateThreads / 32) * 256];
     __shared__ int s_misc[4];
 
     const int r = blockIdx.y;
@@ -289,7 +308,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
     __syncthreads();
     if (!s_misc[2]) return;
     __threadfence();
-    select_row(a, r, s_keys, s_hist, s_misc);
+    select_row(a, r, s_keys, s_hist, s_whist, s_misc);
     if (threadIdx.x == 0) a.ticket[r] = 0;  // self-reset so the workspace is reusable / graph-replayable
 }
 

@@ -11,9 +11,7 @@
 // releases a stage with tcgen05.commit and signals the epilogue through a third barrier.
 // TMA out-of-bounds zero fill handles the M / n_feat / K tails, so any M, K % 8 == 0 and
 // n_feat % 8 == 0 are accepted.
-#include <cuda.h>
-
-#include "et_common.cuh"
+#include "et_tcgen05.cuh"
 
 namespace {
 
@@ -32,89 +30,7 @@ struct LinearArgs {
     int M, K, n_feat, act, k, n_out_rows, is_bf16;
 };
 
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug traps (kernel error) instead of hanging the device.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long start = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - start > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        :
-        : "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                                uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :
-        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_load_32x32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major operand tile with 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);        // start address        bits [0,14)
-    d |= (uint64_t)1 << 16;                             // leading byte offset  bits [16,30) (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset   bits [32,46)
-    d |= (uint64_t)1 << 46;                             // descriptor version = 1 (sm_100)
-    d |= (uint64_t)2 << 61;                             // layout type 2 = SWIZZLE_128B
-    return d;
-}
-// kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major, M = 128, N = BLOCK_N.
-__device__ __forceinline__ uint32_t umma_idesc(int n, int is_bf16) {
-    uint32_t d = 0;
-    d |= 1u << 4;                          // c_format = F32
-    d |= (is_bf16 ? 1u : 0u) << 7;         // a_format
-    d |= (is_bf16 ? 1u : 0u) << 10;        // b_format
-    d |= (uint32_t)(n >> 3) << 17;         // n_dim
-    d |= (uint32_t)(BLOCK_M >> 4) << 24;   // m_dim
-    return d;
-}
+using namespace et_tc;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
@@ -264,37 +180,6 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// 2-D row-major (rows, cols) 16-bit tensor, box (box_rows, 64 cols), 128-byte swizzle
-int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int is_bf16) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (fn == nullptr) return et_fail(ET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return et_fail(ET_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return ET_OK;
-}
-
 template <int BLOCK_N, int STAGES>
 int launch_linear(const void* A, const void* W, const LinearArgs& args, cudaStream_t stream) {
     using L = GemmSmem<BLOCK_N, STAGES>;
@@ -306,9 +191,9 @@ int launch_linear(const void* A, const void* W, const LinearArgs& args, cudaStre
         configured = true;
     }
     CUtensorMap ta, tw;
-    int rc = make_tmap(&ta, A, args.M, args.K, BLOCK_M, args.is_bf16);
+    int rc = make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M, args.is_bf16);
     if (rc) return rc;
-    rc = make_tmap(&tw, W, args.n_feat, args.K, BLOCK_N, args.is_bf16);
+    rc = make_tmap_2d(&tw, W, args.n_feat, args.K, BLOCK_N, args.is_bf16);
     if (rc) return rc;
     dim3 grid((args.n_feat + BLOCK_N - 1) / BLOCK_N, (args.M + BLOCK_M - 1) / BLOCK_M);
     linear_tcgen05_kernel<BLOCK_N, STAGES><<<grid, kGemmThreads, L::TOTAL, stream>>>(ta, tw, args);

@@ -95,7 +95,8 @@ int et_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* 
 /* e = c - p (modules.py:149) for the generic (user-defined policy) gate path. */
 int et_sub(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
 
-/* Test / tuning hook: key 1 forces the GEMM tile width BLOCK_N (0 = automatic). */
+/* Test / tuning hook: key 1 forces the GEMM tile width BLOCK_N (0 = automatic); key 2 = 0 routes global
+ * attention through the mma.sync kernels even where the tcgen05 kernels apply (1 = default). */
 int et_debug_set(int key, long long value);
 
 /*

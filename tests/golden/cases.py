@@ -10,6 +10,10 @@ TINY_GLOBAL = dict(depth=2, dim=32, heads=2, mlp_ratio=4, position_encoding_size
 SMALL_B = dict(depth=3, dim=768, heads=12, mlp_ratio=4, position_encoding_size=(14, 14),
                window_indices=(0, 2), window_size=(14, 14), relative_embedding_size=(64, 64))
 
+# no rel-pos: the reference's interpolation path (utils.py:179) only works for square global grids
+SMALL_TC = dict(depth=3, dim=768, heads=12, mlp_ratio=4, position_encoding_size=(14, 14),
+                window_indices=(0, 2), window_size=(14, 14))
+
 CASES = {
     # windowed (padded 7->8) + global eventful blocks, rel-pos with interpolated tables
     "tiny_vitdet": dict(cfg=TINY, input_size=(7, 7), batch=1, frames=5, policy=("topk", dict(k=12)),
@@ -43,6 +47,10 @@ CASES = {
     "small_vitdet_b": dict(cfg=SMALL_B, input_size=(16, 16), batch=1, frames=3, policy=("topk", dict(k=64)),
                            block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
                            std=0.04, stream="drift", seed=11, subsample=True),
+    # 64-wide token grid, N = 512: the global block takes the tcgen05 attention kernels
+    "small_vitdet_tc": dict(cfg=SMALL_TC, input_size=(8, 64), batch=2, frames=3, policy=("topk", dict(k=160)),
+                            block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
+                            std=0.04, stream="drift", seed=12, subsample=True),
 }
 
 GATES = ("qkv_gate", "projection_gate", "mlp_gate")

@@ -27,11 +27,16 @@ REFERENCE = os.environ.get("ET_REFERENCE", "/root/reference")
 
 for name in ("matplotlib", "matplotlib.pyplot"):  # utils/image.py:1 imports it; unused on this path
     sys.modules.setdefault(name, types.ModuleType(name))
-sys.path.insert(0, REFERENCE)
-sys.path.insert(0, os.path.join(ROOT, "eventful-transformer_b200"))
 sys.path.insert(0, HERE)
+sys.path.insert(0, REFERENCE)
+# The product package directory must NOT be on sys.path here: it is a regular package and would shadow
+# the reference's namespace package `eventful_transformer`. Load the synthetic-input helper by file path.
+import importlib.util  # noqa: E402
 
-import et_synthetic as syn  # noqa: E402
+_spec = importlib.util.spec_from_file_location(
+    "et_synthetic", os.path.join(ROOT, "eventful-transformer_b200", "et_synthetic.py"))
+syn = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(syn)
 from cases import CASES, GATES, n_tokens  # noqa: E402
 
 from eventful_transformer import backbones as ref_backbones  # noqa: E402

@@ -65,6 +65,9 @@ def test_small_dense_attention(dim, heads, grid, rel, cls_token):
 
 
 GLOBAL_CASES = [  # dim, heads, grid, rel, extra tokens, k, batch
+    (768, 12, (4, 64), (4, 64), 0, 100, 2),       # tcgen05 path (64-wide grid, N % 128 == 0), ragged k, batch 2
+    (768, 12, (8, 64), (8, 64), 0, 512, 1),       # tcgen05 path, k == N
+    (128, 2, (2, 64), None, 0, 37, 3),            # tcgen05 path without rel-pos
     (768, 12, (32, 32), (64, 64), 0, 300, 1),     # interpolated rel tables, ragged k
     (768, 12, (14, 14), None, 1, 64, 3),          # ViViT shape: 197 tokens incl. class token, batch of views
     (32, 2, (7, 7), (5, 5), 0, 12, 2),            # dh = 16, N not a multiple of 8
@@ -122,3 +125,38 @@ def test_delta_with_static_input_is_exactly_stationary():
     idx = torch.randperm(256, generator=torch.Generator().manual_seed(6))[:100].view(1, -1).to(DEV)
     again = blk._attention_incremental(qkv, idx)
     assert torch.equal(first, again)
+
+
+@pytest.mark.parametrize("rel", [(16, 64), None])
+def test_tensor_core_path_agrees_with_mma_sync_path(rel):
+    """The tcgen05 kernels and the mma.sync kernels implement the same function: run both on identical inputs."""
+    dim, heads, grid, k = 768, 12, (16, 64), 333
+    n = grid[0] * grid[1]
+    params = block_params(dim, heads, rel, seed=17, std=0.2)
+    g = torch.Generator().manual_seed(8)
+    qkv0 = torch.randn(2, n, 3 * dim, generator=g).to(DT).to(DEV)
+    idx = torch.stack([torch.randperm(n, generator=g)[:k] for _ in range(2)]).to(DEV)
+    qkv1 = qkv0.clone()
+    qkv1.scatter_(1, idx.unsqueeze(-1).expand(-1, -1, 3 * dim), torch.randn(2, k, 3 * dim, generator=g).to(DT).to(DEV))
+    results = []
+    try:
+        for flag in (1, 0):
+            native.lib().et_debug_set(2, flag)
+            blk = gpu_block("EventfulBlock", dim, heads, grid, params, rel=rel)
+            first = blk._attention_first(qkv0, None).clone()
+            second = blk._attention_incremental(qkv1, idx).clone()
+            results.append((first, second, blk.matmul_gate.p.clone(), blk._acc.clone()))
+    finally:
+        native.lib().et_debug_set(2, 1)
+    for a, b in zip(*results):
+        assert rel_err(a, b) < 1.5e-2
+
+
+def test_tensor_core_dense_global_attention():
+    dim, heads, grid, rel = 768, 12, (8, 64), (8, 64)
+    params = block_params(dim, heads, rel, seed=19)
+    qkv = torch.randn(2, 512, 3 * dim, generator=torch.Generator().manual_seed(9)).to(DT)
+    oracle = one_block_oracle(params, dim, heads, grid, orc.DENSE, rel=rel)
+    want = oracle._attention_dense(0, qkv.float())
+    blk = gpu_block("EventfulMatmul1Block", dim, heads, grid, params, rel=rel)
+    assert rel_err(blk._attention_incremental(qkv.to(DEV), None).cpu(), want) < 2e-2

@@ -57,7 +57,7 @@ def test_backbone_matches_oracle_given_identical_index_sets(name):
                 assert set(exact_free) == set(forced)
 
 
-@pytest.mark.parametrize("name", ["tiny_vitdet", "tiny_vivit", "small_vitdet_b", "tiny_dense"])
+@pytest.mark.parametrize("name", ["tiny_vitdet", "tiny_vivit", "small_vitdet_b", "small_vitdet_tc", "tiny_dense"])
 def test_first_frame_matches_reference_fixture(name):
     """Frame 0 needs no selection: compare straight against the committed reference outputs."""
     case, gold = CASES[name], load_golden(name)
@@ -68,7 +68,7 @@ def test_first_frame_matches_reference_fixture(name):
     assert rel_err(got, want) < 0.04
 
 
-@pytest.mark.parametrize("name", ["tiny_vitdet", "small_vitdet_b", "tiny_vivit"])
+@pytest.mark.parametrize("name", ["tiny_vitdet", "small_vitdet_b", "small_vitdet_tc", "tiny_vivit"])
 def test_counters_match_reference_fixture(name):
     case, gold = CASES[name], load_golden(name)
     model = build_gpu_backbone(case, case_params(case), DT)
@@ -84,7 +84,7 @@ def test_counters_match_reference_fixture(name):
             assert {k for k, v in got.items() if v} <= keys
 
 
-@pytest.mark.parametrize("name", ["tiny_vitdet", "small_vitdet_b"])
+@pytest.mark.parametrize("name", ["tiny_vitdet", "small_vitdet_b", "small_vitdet_tc"])
 def test_cuda_graph_replay_is_bit_identical_to_eager(name):
     case = dict(CASES[name], frames=6)
     params, frames = case_params(case), case_frames(dict(CASES[name], frames=6))
