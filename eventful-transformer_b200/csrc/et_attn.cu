@@ -15,6 +15,11 @@
 
 #include "et_common.cuh"
 
+int et_tc_global_attention(const void* qkv, const void* sel, const void* bias_h, const void* bias_w, int mode,
+                           const long long* idx, int k, void* a_state, void* acc, void* out, float* stats, int B, int N,
+                           int NP, int H, int gh, int gw, int is_bf16, cudaStream_t stream);
+int g_attn_tc = 1;  // et_debug_set(2, 0) forces the mma.sync kernels (tests compare the two paths)
+
 namespace {
 
 constexpr int kAttnThreads = 128;  // 4 warps x 16 query rows
@@ -641,8 +646,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_apply_kernel(const AttnArgs
 // ---------------------------------------------------------------- v gate
 // DELTA: for each selected row: dV = v - p_v, Vd = v - dV, p_v = v.   FIRST: p_v = v for every token.
 template <typename T>
-__global__ void __launch_bounds__(256) vgate_kernel(const T* qkv, T* v_state, const long long* idx, T* dV, T* Vd, int N,
-                                                    int D, int k, long long total_vec) {
+__global__ void __launch_bounds__(256) vgate_kernel(const T* qkv, T* v_state, const long long* idx, T* Ksel, T* dV, T* Vd,
+                                                    int N, int D, int k, long long total_vec) {
     const int nch = D / 8;
     for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total_vec;
          gi += (long long)gridDim.x * blockDim.x) {
@@ -653,6 +658,7 @@ __global__ void __launch_bounds__(256) vgate_kernel(const T* qkv, T* v_state, co
         const size_t src = ((size_t)b * N + tok) * 3 * D + 2 * D + (size_t)ch * 8;
         const size_t st = ((size_t)b * N + tok) * D + (size_t)ch * 8;
         const uint4 vraw = ld16(qkv + src);
+        if (Ksel != nullptr) st16(Ksel + (size_t)row * D + (size_t)ch * 8, ld16(qkv + src - D));  // compact k rows
         if (dV != nullptr) {
             float vn[8], pv[8], d[8], r[8];
             unpack16<T>(vraw, vn);
@@ -727,8 +733,11 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     // workspace layout: [bias_h | bias_w | dV | Vd]
     T* bh = static_cast<T*>(ws);
     T* bw = bh + (rel_y ? align8((size_t)a.B * a.H * a.N * a.gh) : 0);
-    T* dV = bw + (rel_y ? align8((size_t)a.B * a.H * a.N * a.gw) : 0);
-    T* Vd = dV + align8((size_t)a.B * a.k * D);
+    T* Ksel = bw + (rel_y ? align8((size_t)a.B * a.H * a.N * a.gw) : 0);
+    T* dV = Ksel + (size_t)a.B * a.k * D;
+    T* Vd = dV + (size_t)a.B * a.k * D;
+    // tensor-core path: dh = 64, 128-row query blocks, rel-pos bias only for the 64-wide grid
+    const bool use_tc = DH == 64 && a.N % 128 == 0 && (rel_y == nullptr || (a.gw == 64 && a.gh <= 64)) && g_attn_tc;
     if (rel_y != nullptr) {
         relpos_bias_kernel<T, DH><<<dim3(a.gh + a.gw, a.H, a.B), kAttnThreads, 0, s>>>(
             a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw);
@@ -740,16 +749,21 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     if (a.mode == ET_ATTN_DELTA) {
         const long long total = (long long)a.B * a.k * (D / 8);
         if (total > 0)
-            vgate_kernel<T><<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, static_cast<T*>(v_state), a.idx, dV, Vd, a.N, D,
-                                                                      a.k, total);
+            vgate_kernel<T><<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, static_cast<T*>(v_state), a.idx,
+                                                                      use_tc ? Ksel : nullptr, dV, Vd, a.N, D, a.k, total);
         ET_COUNT_LAUNCH(1);
         args.dV = dV;
         args.Vd = Vd;
     } else if (a.mode == ET_ATTN_FIRST) {
         const long long total = (long long)a.B * a.N * (D / 8);
         vgate_kernel<T><<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, static_cast<T*>(v_state), nullptr, nullptr, nullptr,
-                                                                  a.N, D, a.N, total);
+                                                                  nullptr, a.N, D, a.N, total);
         ET_COUNT_LAUNCH(1);
+    }
+    if (use_tc) {
+        if (a.mode == ET_ATTN_DELTA && a.k == 0) return ET_OK;
+        return et_tc_global_attention(a.qkv, Ksel, args.bias_h, args.bias_w, a.mode, a.idx, a.k, a.a_state, a.acc, a.out,
+                                      a.stats, a.B, a.N, a.NP, a.H, a.gh, a.gw, std::is_same_v<T, __nv_bfloat16> ? 1 : 0, s);
     }
     const dim3 grid((a.N + BQ - 1) / BQ, a.H, a.B);
     const int smem_a = (BQ * (DH + 8) + BKV * (DH + 8) + BQ * (a.gh + 1 + a.gw + 1)) * (int)sizeof(T) + 16;
@@ -795,7 +809,7 @@ int64_t et_attn_workspace_bytes(int64_t B, int64_t N, int64_t gh, int64_t gw, in
         if (has_relpos) elems += align8(B * nw * heads * wh * ww * wh) + align8(B * nw * heads * wh * ww * ww);
     } else {
         if (has_relpos) elems += align8(B * heads * N * gh) + align8(B * heads * N * gw);
-        elems += 2 * align8(B * k * heads * dh);
+        elems += 3 * align8(B * k * heads * dh);
     }
     return elems * 2 + 256;
 }

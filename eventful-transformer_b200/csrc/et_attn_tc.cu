@@ -37,8 +37,6 @@ struct TcArgs {
     float c1;  // (1 / sqrt(dh)) * log2(e)
 };
 
-__device__ __forceinline__ float bf16_bits_to_float(uint32_t hi16) { return __uint_as_float(hi16 << 16); }
-
 template <bool BF16>
 __device__ __forceinline__ float elem_to_float(uint16_t raw) {
     if constexpr (BF16) return __uint_as_float((uint32_t)raw << 16);
@@ -412,7 +410,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (lane == 0) mbar_arrive(smem_u32(&s_empty[u]));
             const int* tk = s_tok + u * AP_KEYS;
             // normalised attention values of the selected columns, rounded to dtype exactly as stored in the state
-            uint16_t an[64];
+            uint32_t an[32], ad[32];  // bf16/fp16 pairs: element j in half (j & 1) of word j >> 1
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
                 float bias = 0.f;
@@ -420,22 +418,26 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     bias = (elem_to_float<BF16>(brow[s_ky[u * AP_KEYS + j]]) +
                             elem_to_float<BF16>(brow[a.gh + s_kx[u * AP_KEYS + j]])) * kLog2e;
                 const float p = exp2f(fmaf(__uint_as_float(v[j]), a.c1, bias) - m2) * linv;
-                an[j] = tk[j] >= 0 ? float_to_elem<BF16>(p) : (uint16_t)0;
+                const uint32_t e = tk[j] >= 0 ? (uint32_t)float_to_elem<BF16>(p) : 0u;
+                if (j & 1) an[j >> 1] |= e << 16;
+                else an[j >> 1] = e;
             }
-            uint16_t ad[64];
             if (MODE == ET_ATTN_DELTA) {
                 mbar_wait(smem_u32(&ps_full[u]), ph);
                 uint16_t* pt = Pt(u) + row;
 #pragma unroll
                 for (int j = 0; j < 64; ++j) {
+                    const uint16_t cur = (uint16_t)((an[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
                     const float prev = tk[j] >= 0 ? elem_to_float<BF16>(pt[j * QROWS]) : 0.f;
-                    ad[j] = float_to_elem<BF16>(elem_to_float<BF16>(an[j]) - prev);  // dA = a_n - p   (modules.py:196)
-                    pt[j * QROWS] = an[j];                                             // p[:, idx] = a_n (modules.py:200)
+                    const uint32_t d = float_to_elem<BF16>(elem_to_float<BF16>(cur) - prev);  // dA = a_n - p (modules.py:196)
+                    if (j & 1) ad[j >> 1] |= d << 16;
+                    else ad[j >> 1] = d;
+                    pt[j * QROWS] = cur;                                                       // p[:, idx] = a_n (modules.py:200)
                 }
             } else if (MODE == ET_ATTN_FIRST) {
                 uint16_t* pt = Pt(u) + row;
 #pragma unroll
-                for (int j = 0; j < 64; ++j) pt[j * QROWS] = an[j];
+                for (int j = 0; j < 64; ++j) pt[j * QROWS] = (uint16_t)((an[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
             }
             if (t >= 2) mbar_wait(smem_u32(&pv_done[u]), ph ^ 1);  // the P tiles of tile t-2 have been consumed
             // P tiles as K-major, 128-byte-swizzled A operands: row r, 16-byte chunk c -> c ^ (r % 8)
@@ -445,8 +447,9 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const int sw = (c ^ (row & 7)) * 16;
-                    *reinterpret_cast<uint4*>(pn_row + sw) = *reinterpret_cast<const uint4*>(&an[c * 8]);
-                    if (MODE == ET_ATTN_DELTA) *reinterpret_cast<uint4*>(pd_row + sw) = *reinterpret_cast<const uint4*>(&ad[c * 8]);
+                    *reinterpret_cast<uint4*>(pn_row + sw) = make_uint4(an[c * 4], an[c * 4 + 1], an[c * 4 + 2], an[c * 4 + 3]);
+                    if (MODE == ET_ATTN_DELTA)
+                        *reinterpret_cast<uint4*>(pd_row + sw) = make_uint4(ad[c * 4], ad[c * 4 + 1], ad[c * 4 + 2], ad[c * 4 + 3]);
                 }
             }
             fence_proxy_async();  // generic-proxy smem writes -> visible to tcgen05.mma and the bulk stores
@@ -478,17 +481,20 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            uint16_t packed[8];
-            if (MODE == ET_ATTN_DELTA) {
-                const uint4 prev = *reinterpret_cast<const uint4*>(acc + off + c * 8);
-                const uint16_t* pe = reinterpret_cast<const uint16_t*>(&prev);
+            uint32_t w[4];
+            uint4 prev = make_uint4(0, 0, 0, 0);
+            if (MODE == ET_ATTN_DELTA) prev = *reinterpret_cast<const uint4*>(acc + off + c * 8);
+            const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) packed[i] = float_to_elem<BF16>(o[c * 8 + i] + elem_to_float<BF16>(pe[i]));
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) packed[i] = float_to_elem<BF16>(o[c * 8 + i]);
+            for (int i = 0; i < 4; ++i) {
+                float lo = o[c * 8 + 2 * i], hi = o[c * 8 + 2 * i + 1];
+                if (MODE == ET_ATTN_DELTA) {
+                    lo += elem_to_float<BF16>((uint16_t)(pw[i] & 0xffffu));
+                    hi += elem_to_float<BF16>((uint16_t)(pw[i] >> 16));
+                }
+                w[i] = (uint32_t)float_to_elem<BF16>(lo) | ((uint32_t)float_to_elem<BF16>(hi) << 16);
             }
-            const uint4 pk = *reinterpret_cast<const uint4*>(packed);
+            const uint4 pk = make_uint4(w[0], w[1], w[2], w[3]);
             if (MODE != ET_ATTN_DENSE) *reinterpret_cast<uint4*>(acc + off + c * 8) = pk;
             *reinterpret_cast<uint4*>(out + off + c * 8) = pk;
         }

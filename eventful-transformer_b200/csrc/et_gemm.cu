@@ -205,11 +205,17 @@ int g_force_block_n = 0;  // test hook: et_debug_set(1, BLOCK_N)
 
 }  // namespace
 
+extern int g_attn_tc;
+
 extern "C" {
 
 int et_debug_set(int key, long long value) {
     if (key == 1) {
         g_force_block_n = (int)value;
+        return ET_OK;
+    }
+    if (key == 2) {
+        g_attn_tc = value != 0;
         return ET_OK;
     }
     return et_fail(ET_ERR_ARG, "et_debug_set: unknown key %d", key);
