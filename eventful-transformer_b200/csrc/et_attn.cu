@@ -15,7 +15,7 @@
 
 #include "et_common.cuh"
 
-int et_tc_global_attention(const void* qkv, const void* sel, const void* bias_h, const void* bias_w, int mode,
+int et_tc_global_attention(const void* qkv, const void* sel, void* onehot, const void* bias_h, const void* bias_w, int mode,
                            const long long* idx, int k, void* a_state, void* acc, void* out, float* stats, int B, int N,
                            int NP, int H, int gh, int gw, int is_bf16, cudaStream_t stream);
 int g_attn_tc = 1;  // et_debug_set(2, 0) forces the mma.sync kernels (tests compare the two paths)
@@ -184,7 +184,7 @@ __device__ __forceinline__ void add_bias(float (&s)[8][4], const T* bh, const T*
 // bias[token][coord] = q[token] . table[coord]  -> a small tensor-core GEMM per line (mma.sync m16n8k16).
 template <typename T, int DH>
 __global__ void __launch_bounds__(kAttnThreads) relpos_bias_kernel(const AttnArgs a, const T* rel_y, const T* rel_x,
-                                                                    T* bias_h, T* bias_w) {
+                                                                    T* bias_h, T* bias_w, int ld_pad, float scale) {
     constexpr int LD = DH + 8;
     __shared__ __align__(16) T Qs[BQ * LD];
     __shared__ __align__(16) T Ts[BKV * LD];
@@ -228,9 +228,11 @@ __global__ void __launch_bounds__(kAttnThreads) relpos_bias_kernel(const AttnArg
                 for (int i = 0; i < 4; ++i) {
                     const int j = tok0 + warp * 16 + g + (i >> 1) * 8;
                     const int kc = out0 + nt * 8 + tq * 2 + (i & 1);
-                    if (j < ntok && kc < nout) {
+                    const int ld = ld_pad > 0 ? ld_pad : nout;  // ld_pad: tc layout, rows zero padded to ld_pad columns
+                    if (j < ntok && kc < ld) {
                         const int t = ymode ? fixed * lw + j : j * lw + fixed;
-                        dst[(((size_t)bw * a.H + h) * a.Wn + t) * nout + kc] = ElemTraits<T>::from_float(s[nt][i]);
+                        dst[(((size_t)bw * a.H + h) * a.Wn + t) * ld + kc] =
+                            ElemTraits<T>::from_float(kc < nout ? s[nt][i] * scale : 0.f);
                     }
                 }
         }
@@ -713,7 +715,7 @@ int run_window(const AttnArgs& a, const void* rel_y, const void* rel_x, void* bi
         T* bh = static_cast<T*>(bias_ws);
         T* bw = bh + align8((size_t)a.B * nwin * a.H * a.Wn * lh);
         relpos_bias_kernel<T, DH><<<dim3(lh + lw, a.H, a.B * nwin), kAttnThreads, 0, s>>>(
-            a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw);
+            a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw, 0, 1.f);
         ET_COUNT_LAUNCH(1);
         args.bias_h = bh;
         args.bias_w = bw;
@@ -730,17 +732,19 @@ template <typename T, int DH>
 int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_state, void* ws, cudaStream_t s) {
     AttnArgs args = a;
     const int D = a.H * DH;
-    // workspace layout: [bias_h | bias_w | dV | Vd]
-    T* bh = static_cast<T*>(ws);
-    T* bw = bh + (rel_y ? align8((size_t)a.B * a.H * a.N * a.gh) : 0);
-    T* Ksel = bw + (rel_y ? align8((size_t)a.B * a.H * a.N * a.gw) : 0);
-    T* dV = Ksel + (size_t)a.B * a.k * D;
-    T* Vd = dV + (size_t)a.B * a.k * D;
     // tensor-core path: dh = 64, 128-row query blocks, rel-pos bias only for the 64-wide grid
     const bool use_tc = DH == 64 && a.N % 128 == 0 && (rel_y == nullptr || (a.gw == 64 && a.gh <= 64)) && g_attn_tc;
+    // workspace layout: [bias_h | bias_w | K_sel | dV | Vd | onehot]; the tc path pads bias rows to 64 columns
+    const size_t ldh = use_tc ? 64 : a.gh, ldw = use_tc ? 64 : a.gw;
+    T* bh = static_cast<T*>(ws);
+    T* bw = bh + (rel_y ? align8((size_t)a.B * a.H * a.N * ldh) : 0);
+    T* Ksel = bw + (rel_y ? align8((size_t)a.B * a.H * a.N * ldw) : 0);
+    T* dV = Ksel + (size_t)a.B * a.k * D;
+    T* Vd = dV + (size_t)a.B * a.k * D;
+    T* onehot = Vd + (size_t)a.B * a.k * D;
     if (rel_y != nullptr) {
         relpos_bias_kernel<T, DH><<<dim3(a.gh + a.gw, a.H, a.B), kAttnThreads, 0, s>>>(
-            a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw);
+            a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw, use_tc ? 64 : 0, use_tc ? 8.f : 1.f);
         ET_COUNT_LAUNCH(1);
         args.bias_h = bh;
         args.bias_w = bw;
@@ -762,7 +766,7 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     }
     if (use_tc) {
         if (a.mode == ET_ATTN_DELTA && a.k == 0) return ET_OK;
-        return et_tc_global_attention(a.qkv, Ksel, args.bias_h, args.bias_w, a.mode, a.idx, a.k, a.a_state, a.acc, a.out,
+        return et_tc_global_attention(a.qkv, Ksel, onehot, args.bias_h, args.bias_w, a.mode, a.idx, a.k, a.a_state, a.acc, a.out,
                                       a.stats, a.B, a.N, a.NP, a.H, a.gh, a.gw, std::is_same_v<T, __nv_bfloat16> ? 1 : 0, s);
     }
     const dim3 grid((a.N + BQ - 1) / BQ, a.H, a.B);
@@ -808,8 +812,10 @@ int64_t et_attn_workspace_bytes(int64_t B, int64_t N, int64_t gh, int64_t gw, in
         const int64_t nw = ((gh + wh - 1) / wh) * ((gw + ww - 1) / ww);
         if (has_relpos) elems += align8(B * nw * heads * wh * ww * wh) + align8(B * nw * heads * wh * ww * ww);
     } else {
-        if (has_relpos) elems += align8(B * heads * N * gh) + align8(B * heads * N * gw);
+        // upper bound over both layouts (the tensor-core path pads bias rows to 64 columns and adds a one-hot scratch)
+        if (has_relpos) elems += align8(B * heads * N * (gh > 64 ? gh : 64)) + align8(B * heads * N * (gw > 64 ? gw : 64));
         elems += 3 * align8(B * k * heads * dh);
+        elems += ((B * k > N) ? B * k : N) * 128;
     }
     return elems * 2 + 256;
 }

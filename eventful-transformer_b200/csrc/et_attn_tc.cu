@@ -1,39 +1,45 @@
 // Global attention of the Eventful blocks on 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
 // Fast path for dh = 64, N % 128 == 0 and (no rel-pos | 64-wide token grid); everything else takes the
-// mma.sync kernels in et_attn.cu.  Statistics are kept in the log2 domain: m2 = max(x) * log2(e).
+// mma.sync kernels in et_attn.cu.  Statistics are kept in the log2 domain: m2 = reference exponent of the row.
 //
-//   tc_stats_kernel  (phase A)  S = Q K^T per 128 x 128 tile in TMEM (double buffered), softmax warps read
-//                               their own row with tcgen05.ld, add the rel-pos bias held in registers and keep
-//                               the running row max / row sum.  Output: (m2, l) per row.
+//   tc_stats_kernel  (phase A)  S = Q K^T per 128 x 128 tile in TMEM (double buffered); softmax warps read their
+//                               row with tcgen05.ld, add the rel-pos bias (registers) and keep (m2, l) per row.
 //   tc_apply_kernel  (phase B)  per 128-row query block and 64-key tile of the SELECTED keys:
-//                               S = Q K_sel^T (TMEM)  ->  a_n = exp2(S - m2) / l (bf16, exactly as stored)
-//                               A-gate: dA = a_n - a_state[:, idx]; a_state[:, idx] = a_n
-//                                       (column-major state: one 256-byte cp.async.bulk per column each way)
-//                               accumulate: O += a_n . dV + dA . (v_n - dV)  (two tcgen05 MMAs, P from smem,
-//                                       V tiles as MN-major B operands straight from TMA)
+//                               S' = Q' K'^T  with  Q' = [q | 8 bias_h(row) | 8 bias_w(row)],
+//                                                   K' = [k | onehot(key y) | onehot(key x)]
+//                                    so that S' / 8 = q.k / 8 + bias_h[row, ky] + bias_w[row, kx]: the decomposed
+//                                    rel-pos bias (eventful_transformer/utils.py:157-166) comes out of the MMA and the
+//                                    softmax threads do no table lookups;
+//                               a_n = exp2(S' c1 - m2) / l, rounded to dtype exactly as stored in the gate state;
+//                               A-gate: dA = a_n - a_state[:, idx]; a_state[:, idx] = a_n  (column-major state: a
+//                                    selected column is 256 contiguous bytes per query block; 16-byte cp.async in,
+//                                    128-bit stores out, by the producer warp);
+//                               O += a_n . dV + dA . (v_n - dV): two tcgen05 MMAs, P tiles from smem (K-major,
+//                                    128B swizzle), V tiles as MN-major B operands straight from TMA;
 //                               epilogue: acc += O; out = acc.
 //                    FIRST / DENSE modes run the same pipeline over all keys with V from the QKV buffer.
-// Warp roles (192 threads): warp 0 = TMA / bulk-copy producer + state write-back, warp 1 = TMEM allocator and
-// single-thread MMA issuer, warps 2-5 = softmax / gate / epilogue (one query row per thread).
+// Warp roles (320 threads): warp 0 = TMA / cp.async producer + state write-back, warp 1 = TMEM allocator and
+// single-thread MMA issuer, warps 2-9 = softmax / gate / epilogue: two warps per TMEM lane quarter, each thread
+// owns one query row and half of the tile's key columns.
 #include "et_tcgen05.cuh"
 
 using namespace et_tc;
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
 constexpr int QROWS = 128;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct TcArgs {
-    const void* bias_h;
+    const void* bias_h;  // (B, H, N, 64): 8 x bias, zero padded to 64 columns (tc layout)
     const void* bias_w;
     float* stats;
     const long long* idx;
     void* a_state;
     void* acc;
     void* out;
-    int B, N, NP, H, D, gh, gw, k, is_bf16, sel_rows;
+    int B, N, NP, H, D, gh, gw, k, is_bf16, sel_rows, has_bias;
     float c1;  // (1 / sqrt(dh)) * log2(e)
 };
 
@@ -43,18 +49,19 @@ __device__ __forceinline__ float elem_to_float(uint16_t raw) {
     else return __half2float(__ushort_as_half(raw));
 }
 template <bool BF16>
-__device__ __forceinline__ uint16_t float_to_elem(float v) {
-    if constexpr (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
-    else return __half_as_ushort(__float2half_rn(v));
+__device__ __forceinline__ uint32_t float_to_elem(float v) {
+    if constexpr (BF16) return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+    else return (uint32_t)__half_as_ushort(__float2half_rn(v));
 }
 
-__device__ __forceinline__ void named_sync_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void named_sync_softmax() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ============================================================================================= phase A
 constexpr int ST_KEYS = 128;
 constexpr int ST_STAGES = 4;
 constexpr int ST_TILE = ST_KEYS * 64 * 2;  // 16 KB
-constexpr int ST_SMEM = QROWS * 64 * 2 + ST_STAGES * ST_TILE + 256 + 1024;
+constexpr int ST_OFF_X = QROWS * 128 + ST_STAGES * ST_TILE;  // (m2, l) exchange between the two column halves
+constexpr int ST_SMEM = ST_OFF_X + QROWS * 8 + 256 + 1024;
 
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const TcArgs a) {
@@ -62,7 +69,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Qs = smem;
     uint8_t* Ks = smem + QROWS * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Ks + ST_STAGES * ST_TILE);
+    float2* xchg = reinterpret_cast<float2*>(smem + ST_OFF_X);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST_OFF_X + QROWS * 8);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;
     uint64_t* k_empty = k_full + ST_STAGES;
@@ -83,7 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
-            mbar_init(smem_u32(&s_empty[s]), 4);
+            mbar_init(smem_u32(&s_empty[s]), 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -124,65 +132,85 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
         }
     } else {
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;  // key columns [32 half, 32 half + 32) of each 64-wide image row
         const int row = quarter * 32 + lane;
         const size_t grow = ((size_t)b * a.H + h) * a.N + q0 + row;
-        const bool has_bias = a.bias_h != nullptr;
-        // rel-pos bias of this query row, pre-scaled by log2(e): bw for the 64 key columns, bh per key image row
-        float bwl[64];
+        // rel-pos bias of this query row (stored as 8 x bias), in the log2 domain
+        const float bscale = 0.125f * kLog2e;
+        float bwl[32];
         const uint16_t* bh_row = nullptr;
-        if (has_bias) {
-            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.bias_w) + grow * 64);
+        if (a.has_bias) {
+            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.bias_w) + grow * 64 + half * 32);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 const uint4 u4 = src[c];
-                const uint16_t* e = reinterpret_cast<const uint16_t*>(&u4);
+                const uint32_t w[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) bwl[c * 8 + i] = elem_to_float<BF16>(e[i]) * kLog2e;
+                for (int i = 0; i < 4; ++i) {
+                    bwl[c * 8 + 2 * i] = elem_to_float<BF16>((uint16_t)(w[i] & 0xffffu)) * bscale;
+                    bwl[c * 8 + 2 * i + 1] = elem_to_float<BF16>((uint16_t)(w[i] >> 16)) * bscale;
+                }
             }
-            bh_row = static_cast<const uint16_t*>(a.bias_h) + grow * a.gh;
+            bh_row = static_cast<const uint16_t*>(a.bias_h) + grow * 64;
         } else {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) bwl[i] = 0.f;
+            for (int i = 0; i < 32; ++i) bwl[i] = 0.f;
         }
-        float m2 = -INFINITY, l = 0.f;
+        float m2 = -1e30f, l = 0.f;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         for (int t = 0; t < T; ++t) {
             const int u = t & 1;
-            float bh0 = 0.f, bh1 = 0.f;
-            if (has_bias) {  // a 128-key tile spans two image rows of the 64-wide grid
+            float bh2[2] = {0.f, 0.f};
+            if (a.has_bias) {  // a 128-key tile spans two image rows of the 64-wide grid
                 const uint32_t pair = *reinterpret_cast<const uint32_t*>(bh_row + 2 * t);
-                bh0 = elem_to_float<BF16>((uint16_t)(pair & 0xffffu)) * kLog2e;
-                bh1 = elem_to_float<BF16>((uint16_t)(pair >> 16)) * kLog2e;
+                bh2[0] = elem_to_float<BF16>((uint16_t)(pair & 0xffffu)) * bscale;
+                bh2[1] = elem_to_float<BF16>((uint16_t)(pair >> 16)) * bscale;
             }
             mbar_wait(smem_u32(&s_full[u]), (t >> 1) & 1);
             tcgen05_fence_after();
+            uint32_t v0[32], v1[32];
+            tmem_load_32x32(taddr + (uint32_t)(u * ST_KEYS + half * 32), v0);       // image row 2t
+            tmem_load_32x32(taddr + (uint32_t)(u * ST_KEYS + 64 + half * 32), v1);  // image row 2t + 1
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_empty[u]));
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_load_32x32(taddr + (uint32_t)(u * ST_KEYS + c * 32), v);
-                if (c == 3) {  // whole tile read: hand the TMEM buffer back to the MMA warp
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&s_empty[u]));
-                }
-                const float bh = (c < 2) ? bh0 : bh1;
+            for (int c = 0; c < 2; ++c) {
+                const uint32_t* v = c ? v1 : v0;
+                const float bh = bh2[c];
                 float x[32];
-                float cmax = -INFINITY;
+                float cmax = -1e30f;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    x[i] = fmaf(__uint_as_float(v[i]), a.c1, bwl[(c & 1) * 32 + i]) + bh;
+                    x[i] = fmaf(__uint_as_float(v[i]), a.c1, bwl[i]);
                     cmax = fmaxf(cmax, x[i]);
                 }
-                const float mn = fmaxf(m2, cmax);
-                float sum = 0.f;
+                // m2 is a reference exponent, not necessarily the exact row max: it only moves when exceeded by more
+                // than 2^8, so exp2(x - m2) <= 256 stays finite and (m2, l) remain a consistent pair
+                if (cmax + bh > m2 + 8.f) {
+                    l *= ex2_approx(m2 - (cmax + bh));
+                    m2 = cmax + bh;
+                }
+                const float shift = bh - m2;
+                float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) sum += exp2f(x[i] - mn);
-                l = l * exp2f(m2 - mn) + sum;
-                m2 = mn;
+                for (int i = 0; i < 32; i += 2) {
+                    sum0 += ex2_approx(x[i] + shift);
+                    sum1 += ex2_approx(x[i + 1] + shift);
+                }
+                l += sum0 + sum1;
             }
         }
-        a.stats[grow * 2] = m2;
-        a.stats[grow * 2 + 1] = l;
+        // merge the two column halves of each row
+        if (half == 1) xchg[row] = make_float2(m2, l);
+        named_sync_softmax();
+        if (half == 0) {
+            const float2 o = xchg[row];
+            const float mm = fmaxf(m2, o.x);
+            l = l * ex2_approx(m2 - mm) + o.y * ex2_approx(o.x - mm);
+            a.stats[grow * 2] = mm;
+            a.stats[grow * 2 + 1] = l;
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -194,51 +222,48 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
 
 // ============================================================================================= phase B
 constexpr int AP_KEYS = 64;
-constexpr int AP_KV = AP_KEYS * 64 * 2;           // 8 KB: one K / V tile
-constexpr int AP_STAGE = 3 * AP_KV;               // K, V1, V2
+constexpr int AP_BLK = AP_KEYS * 64 * 2;          // 8 KB: one 64-key x 64-column operand block
+constexpr int AP_STAGE = 5 * AP_BLK;              // K, onehot-y, onehot-x, V1, V2
 constexpr int AP_PT = AP_KEYS * QROWS * 2;        // 16 KB: a_state tile [key][row]
 constexpr int AP_P = QROWS * AP_KEYS * 2;         // 16 KB: P tile (A operand)
-constexpr int AP_BIAS_LD = 130;                   // halfwords per bias-table row (odd word count: no bank conflicts)
-constexpr int AP_OFF_ST = QROWS * 128;            // 16 KB Q
+constexpr int AP_OFF_ST = 3 * QROWS * 128;        // Q' = three 16 KB blocks: q, 8 bias_h, 8 bias_w
 constexpr int AP_OFF_PT = AP_OFF_ST + 2 * AP_STAGE;
 constexpr int AP_OFF_P = AP_OFF_PT + 2 * AP_PT;
-constexpr int AP_OFF_BIAS = AP_OFF_P + 4 * AP_P;
-constexpr int AP_OFF_MISC = AP_OFF_BIAS + ((QROWS * AP_BIAS_LD * 2 + 1023) / 1024) * 1024;
-constexpr int AP_SMEM = AP_OFF_MISC + 2048 + 1024;
+constexpr int AP_OFF_MISC = AP_OFF_P + 2 * AP_P;
+constexpr int AP_SMEM = AP_OFF_MISC + 1024 + 1024;
 
 template <bool BF16, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const TcArgs a) {
+tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bw,
+                const __grid_constant__ CUtensorMap tm_oh, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* Qs = smem;
-    auto Kt = [&](int u) { return smem + AP_OFF_ST + u * AP_STAGE; };
-    auto V1 = [&](int u) { return smem + AP_OFF_ST + u * AP_STAGE + AP_KV; };
-    auto V2 = [&](int u) { return smem + AP_OFF_ST + u * AP_STAGE + 2 * AP_KV; };
+    auto Qb = [&](int i) { return smem + i * QROWS * 128; };
+    auto Kb = [&](int u, int i) { return smem + AP_OFF_ST + u * AP_STAGE + i * AP_BLK; };  // 0 k, 1 oh-y, 2 oh-x
+    auto V1 = [&](int u) { return smem + AP_OFF_ST + u * AP_STAGE + 3 * AP_BLK; };
+    auto V2 = [&](int u) { return smem + AP_OFF_ST + u * AP_STAGE + 4 * AP_BLK; };
     auto Pt = [&](int u) { return reinterpret_cast<uint16_t*>(smem + AP_OFF_PT + u * AP_PT); };
-    auto Pn = [&](int u) { return smem + AP_OFF_P + u * 2 * AP_P; };
-    auto Pd = [&](int u) { return smem + AP_OFF_P + u * 2 * AP_P + AP_P; };
-    uint16_t* bias_tab = reinterpret_cast<uint16_t*>(smem + AP_OFF_BIAS);
-    int* s_tok = reinterpret_cast<int*>(smem + AP_OFF_MISC);           // [2][64]
-    uint8_t* s_ky = reinterpret_cast<uint8_t*>(s_tok + 2 * AP_KEYS);    // [2][64]
-    uint8_t* s_kx = s_ky + 2 * AP_KEYS;                                 // [2][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AP_OFF_MISC + 1024);
+    uint8_t* Pn = smem + AP_OFF_P;
+    uint8_t* Pd = smem + AP_OFF_P + AP_P;
+    int* s_tok = reinterpret_cast<int*>(smem + AP_OFF_MISC);  // [2][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AP_OFF_MISC + 512);
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;
     uint64_t* ps_full = bars + 3;
     uint64_t* s_full = bars + 5;
     uint64_t* s_empty = bars + 7;
-    uint64_t* p_ready = bars + 9;
-    uint64_t* pv_done = bars + 11;
-    uint64_t* ps_done = bars + 13;
-    uint64_t* o_full = bars + 15;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* p_ready = bars + 9;   // single P buffer: one barrier, one phase per tile
+    uint64_t* pv_done = bars + 10;  // [2]: PV MMAs of tile t commit to slot t & 1 (at most one phase outstanding each)
+    uint64_t* ps_done = bars + 12;  // [2]
+    uint64_t* o_full = bars + 14;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * QROWS, h = blockIdx.y, b = blockIdx.z;
     const int nkeys = (MODE == ET_ATTN_DELTA) ? a.k : a.N;
     const int T = (nkeys + AP_KEYS - 1) / AP_KEYS;
-    const bool has_bias = a.bias_h != nullptr;
+    const int nkb = a.has_bias ? 3 : 1;  // 64-column blocks of the augmented reduction dimension
     uint16_t* a_state = static_cast<uint16_t*>(a.a_state);
     const size_t a_head = ((size_t)b * a.H + h) * (size_t)a.N * a.NP;
 
@@ -247,14 +272,14 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_kv) : "memory");
         mbar_init(smem_u32(q_full), 1);
         mbar_init(smem_u32(o_full), 1);
+        mbar_init(smem_u32(p_ready), 8);
         for (int u = 0; u < 2; ++u) {
             mbar_init(smem_u32(&kv_full[u]), 1);
-            mbar_init(smem_u32(&ps_full[u]), 1);
+            mbar_init(smem_u32(&ps_full[u]), 32);  // one cp.async arrival per producer lane
             mbar_init(smem_u32(&s_full[u]), 1);
-            mbar_init(smem_u32(&s_empty[u]), 4);
-            mbar_init(smem_u32(&p_ready[u]), 4);
+            mbar_init(smem_u32(&s_empty[u]), 8);
+            mbar_init(smem_u32(&ps_done[u]), 8);
             mbar_init(smem_u32(&pv_done[u]), 1);
-            mbar_init(smem_u32(&ps_done[u]), 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -268,94 +293,104 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (warp == 0) {
         // ------------------------------------------------------------------ producer + state write-back
         if (lane == 0) {
-            mbar_expect_tx(smem_u32(q_full), QROWS * 128);
-            tma_load_2d(smem_u32(Qs), &tm_q, smem_u32(q_full), h * 64, b * a.N + q0);
+            const int qrow = b * a.N + q0;
+            mbar_expect_tx(smem_u32(q_full), nkb * QROWS * 128);
+            tma_load_2d(smem_u32(Qb(0)), &tm_q, smem_u32(q_full), h * 64, qrow);
+            if (a.has_bias) {
+                const int brow = (b * a.H + h) * a.N + q0;
+                tma_load_2d(smem_u32(Qb(1)), &tm_bh, smem_u32(q_full), 0, brow);
+                tma_load_2d(smem_u32(Qb(2)), &tm_bw, smem_u32(q_full), 0, brow);
+            }
         }
+        // one selected column x this CTA's 128 rows = 256 contiguous bytes = 16 lanes x 16 B: two columns per warp op
+        const int sub = lane >> 4, seg = (lane & 15) * 8;
         auto write_back = [&](int tt) {  // a_state[:, idx of tile tt] <- a_n (softmax warps left it in Pt)
             const int u = tt & 1;
             mbar_wait(smem_u32(&ps_done[u]), (tt >> 1) & 1);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int j = lane + half * 32;
+#pragma unroll 8
+            for (int i = 0; i < AP_KEYS / 2; ++i) {
+                const int j = 2 * i + sub;
                 const int tok = s_tok[u * AP_KEYS + j];
-                if (tok >= 0) bulk_store(a_state + a_head + (size_t)tok * a.NP + q0, smem_u32(Pt(u) + j * QROWS), QROWS * 2);
+                if (tok >= 0)
+                    *reinterpret_cast<uint4*>(a_state + a_head + (size_t)tok * a.NP + q0 + seg) =
+                        *reinterpret_cast<const uint4*>(Pt(u) + j * QROWS + seg);
             }
-            bulk_commit();
         };
         for (int t = 0; t < T; ++t) {
             const int u = t & 1, key0 = t * AP_KEYS;
-            if (t >= 2) mbar_wait(smem_u32(&pv_done[u]), ((t >> 1) & 1) ^ 1);  // tile t-2 fully consumed
-            if (MODE != ET_ATTN_DENSE) bulk_wait_read_all();                    // its write-back has left smem
-            int tok[2];
+            if (t >= 2) mbar_wait(smem_u32(&pv_done[u]), ((t >> 1) & 1) ^ 1);  // tile t-2: the MMAs are done with slot u
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int j = key0 + lane + half * 32;
-                tok[half] = -1;
-                if (j < nkeys) tok[half] = (MODE == ET_ATTN_DELTA) ? (int)a.idx[(size_t)b * a.k + j] : j;
-                s_tok[u * AP_KEYS + lane + half * 32] = tok[half];
-                if (has_bias && tok[half] >= 0) {
-                    s_ky[u * AP_KEYS + lane + half * 32] = (uint8_t)(tok[half] / a.gw);
-                    s_kx[u * AP_KEYS + lane + half * 32] = (uint8_t)(tok[half] % a.gw);
-                }
+                int tok = -1;
+                if (j < nkeys) tok = (MODE == ET_ATTN_DELTA) ? (int)a.idx[(size_t)b * a.k + j] : j;
+                s_tok[u * AP_KEYS + lane + half * 32] = tok;
             }
             __syncwarp();
             if (lane == 0) {
                 const uint32_t fb = smem_u32(&kv_full[u]);
+                const int nblk = nkb + (MODE == ET_ATTN_DELTA ? 2 : 1);
+                mbar_expect_tx(fb, nblk * AP_BLK);
+                const int orow = (MODE == ET_ATTN_DELTA) ? b * a.k + key0 : key0;
                 if (MODE == ET_ATTN_DELTA) {
-                    mbar_expect_tx(fb, 3 * AP_KV);
                     const int r0 = b * a.k + key0;
-                    tma_load_2d(smem_u32(Kt(u)), &tm_kv, fb, h * 64, r0);
+                    tma_load_2d(smem_u32(Kb(u, 0)), &tm_kv, fb, h * 64, r0);
                     tma_load_2d(smem_u32(V1(u)), &tm_kv, fb, h * 64, a.sel_rows + r0);
                     tma_load_2d(smem_u32(V2(u)), &tm_kv, fb, h * 64, 2 * a.sel_rows + r0);
-                    const int nvalid = min(AP_KEYS, nkeys - key0);
-                    mbar_expect_tx(smem_u32(&ps_full[u]), (uint32_t)nvalid * QROWS * 2);
                 } else {
-                    mbar_expect_tx(fb, 2 * AP_KV);
-                    tma_load_2d(smem_u32(Kt(u)), &tm_kv, fb, a.D + h * 64, b * a.N + key0);
+                    tma_load_2d(smem_u32(Kb(u, 0)), &tm_kv, fb, a.D + h * 64, b * a.N + key0);
                     tma_load_2d(smem_u32(V1(u)), &tm_kv, fb, 2 * a.D + h * 64, b * a.N + key0);
                 }
+                if (a.has_bias) {
+                    tma_load_2d(smem_u32(Kb(u, 1)), &tm_oh, fb, 0, orow);
+                    tma_load_2d(smem_u32(Kb(u, 2)), &tm_oh, fb, 64, orow);
+                }
             }
-            __syncwarp();
-            if (MODE == ET_ATTN_DELTA) {
-#pragma unroll
-                for (int half = 0; half < 2; ++half)
-                    if (tok[half] >= 0)
-                        bulk_load(smem_u32(Pt(u) + (lane + half * 32) * QROWS),
-                                  a_state + a_head + (size_t)tok[half] * a.NP + q0, QROWS * 2, smem_u32(&ps_full[u]));
+            if (MODE == ET_ATTN_DELTA) {  // previous attention values of the selected columns -> smem tile [key][row]
+#pragma unroll 8
+                for (int i = 0; i < AP_KEYS / 2; ++i) {
+                    const int j = 2 * i + sub;
+                    const int tj = s_tok[u * AP_KEYS + j];
+                    if (tj >= 0)
+                        cp_async_16(smem_u32(Pt(u) + j * QROWS + seg), a_state + a_head + (size_t)tj * a.NP + q0 + seg);
+                }
+                cp_async_arrive_noinc(smem_u32(&ps_full[u]));
             }
             if (MODE != ET_ATTN_DENSE && t >= 1) write_back(t - 1);
         }
         if (MODE != ET_ATTN_DENSE && T >= 1) write_back(T - 1);
-        bulk_wait_all();
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc_ex(128, AP_KEYS, a.is_bf16, 0);
             const uint32_t idesc_o = umma_idesc_ex(128, 64, a.is_bf16, 1);  // B = V tile, MN-major
             mbar_wait(smem_u32(q_full), 0);
-            const uint64_t dq = umma_smem_desc(smem_u32(Qs));
             auto issue_s = [&](int t) {
                 const int u = t & 1;
                 mbar_wait(smem_u32(&kv_full[u]), (t >> 1) & 1);
                 mbar_wait(smem_u32(&s_empty[u]), ((t >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
-                const uint64_t dk = umma_smem_desc(smem_u32(Kt(u)));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint64_t dq = umma_smem_desc(smem_u32(Qb(kb)));
+                    const uint64_t dk = umma_smem_desc(smem_u32(Kb(u, kb)));
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    tcgen05_mma_f16(tmem_base + u * AP_KEYS, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s, kk > 0);
+                    for (int kk = 0; kk < 4; ++kk)
+                        tcgen05_mma_f16(tmem_base + u * AP_KEYS, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s,
+                                        (kb > 0 || kk > 0));
+                }
                 tcgen05_commit(smem_u32(&s_full[u]));
             };
             auto issue_pv = [&](int t) {
                 const int u = t & 1;
-                mbar_wait(smem_u32(&p_ready[u]), (t >> 1) & 1);
+                mbar_wait(smem_u32(p_ready), t & 1);
                 tcgen05_fence_after();
-                const uint64_t dpn = umma_smem_desc(smem_u32(Pn(u)));
+                const uint64_t dpn = umma_smem_desc(smem_u32(Pn));
                 const uint64_t dv1 = umma_smem_desc_mn(smem_u32(V1(u)));
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)  // 16 keys per step: +32 B in P rows, +16 rows (2048 B) in the V tile
                     tcgen05_mma_f16(tmem_o, dpn + (uint64_t)(2 * kk), dv1 + (uint64_t)(128 * kk), idesc_o, (t > 0 || kk > 0));
                 if (MODE == ET_ATTN_DELTA) {
-                    const uint64_t dpd = umma_smem_desc(smem_u32(Pd(u)));
+                    const uint64_t dpd = umma_smem_desc(smem_u32(Pd));
                     const uint64_t dv2 = umma_smem_desc_mn(smem_u32(V2(u)));
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
@@ -373,126 +408,100 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     } else {
         // ------------------------------------------------------------------ softmax / gate / epilogue
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;  // key columns [32 half, +32) of every 64-key tile
         const int row = quarter * 32 + lane;
         const size_t grow = ((size_t)b * a.H + h) * a.N + q0 + row;
-        const int wtab = a.gh + a.gw;
-        if (has_bias) {  // this CTA's 128 bias rows -> padded smem table [row][bh | bw]
-            const uint16_t* gbh = static_cast<const uint16_t*>(a.bias_h) + (grow - row) * a.gh;
-            const uint16_t* gbw = static_cast<const uint16_t*>(a.bias_w) + (grow - row) * a.gw;
-            const int tid = threadIdx.x - 64;
-            for (int i = tid; i < QROWS * a.gh; i += 128) bias_tab[(i / a.gh) * AP_BIAS_LD + i % a.gh] = gbh[i];
-            for (int i = tid; i < QROWS * a.gw; i += 128) bias_tab[(i / a.gw) * AP_BIAS_LD + a.gh + i % a.gw] = gbw[i];
-            named_sync_softmax();
-        }
-        (void)wtab;
         const float m2 = a.stats[grow * 2];
         const float linv = 1.f / a.stats[grow * 2 + 1];
-        const uint16_t* brow = bias_tab + row * AP_BIAS_LD;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint8_t* pn_row = Pn + (row >> 3) * 1024 + (row & 7) * 128;
+        uint8_t* pd_row = Pd + (row >> 3) * 1024 + (row & 7) * 128;
         for (int t = 0; t < T; ++t) {
             const int u = t & 1;
             const uint32_t ph = (t >> 1) & 1;
             mbar_wait(smem_u32(&s_full[u]), ph);
             tcgen05_fence_after();
-            uint32_t v[64];
-            {
-                uint32_t lo[32], hi[32];
-                tmem_load_32x32(taddr + (uint32_t)(u * AP_KEYS), lo);
-                tmem_load_32x32(taddr + (uint32_t)(u * AP_KEYS + 32), hi);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    v[i] = lo[i];
-                    v[32 + i] = hi[i];
-                }
-            }
+            uint32_t v[32];
+            tmem_load_32x32(taddr + (uint32_t)(u * AP_KEYS + half * 32), v);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_empty[u]));
-            const int* tk = s_tok + u * AP_KEYS;
+            const int* tk = s_tok + u * AP_KEYS + half * 32;
             // normalised attention values of the selected columns, rounded to dtype exactly as stored in the state
-            uint32_t an[32], ad[32];  // bf16/fp16 pairs: element j in half (j & 1) of word j >> 1
+            uint32_t an[16], ad[16];  // element pairs: key 2i in the low half of word i
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                float bias = 0.f;
-                if (has_bias)
-                    bias = (elem_to_float<BF16>(brow[s_ky[u * AP_KEYS + j]]) +
-                            elem_to_float<BF16>(brow[a.gh + s_kx[u * AP_KEYS + j]])) * kLog2e;
-                const float p = exp2f(fmaf(__uint_as_float(v[j]), a.c1, bias) - m2) * linv;
-                const uint32_t e = tk[j] >= 0 ? (uint32_t)float_to_elem<BF16>(p) : 0u;
-                if (j & 1) an[j >> 1] |= e << 16;
-                else an[j >> 1] = e;
+            for (int i = 0; i < 16; ++i) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), a.c1, -m2)) * linv;
+                const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), a.c1, -m2)) * linv;
+                const uint32_t e0 = tk[2 * i] >= 0 ? float_to_elem<BF16>(p0) : 0u;
+                const uint32_t e1 = tk[2 * i + 1] >= 0 ? float_to_elem<BF16>(p1) : 0u;
+                an[i] = e0 | (e1 << 16);
             }
             if (MODE == ET_ATTN_DELTA) {
                 mbar_wait(smem_u32(&ps_full[u]), ph);
-                uint16_t* pt = Pt(u) + row;
+                uint16_t* pt = Pt(u) + (half * 32) * QROWS + row;
 #pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                    const uint16_t cur = (uint16_t)((an[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
-                    const float prev = tk[j] >= 0 ? elem_to_float<BF16>(pt[j * QROWS]) : 0.f;
-                    const uint32_t d = float_to_elem<BF16>(elem_to_float<BF16>(cur) - prev);  // dA = a_n - p (modules.py:196)
-                    if (j & 1) ad[j >> 1] |= d << 16;
-                    else ad[j >> 1] = d;
-                    pt[j * QROWS] = cur;                                                       // p[:, idx] = a_n (modules.py:200)
+                for (int i = 0; i < 16; ++i) {
+                    const uint16_t c0 = (uint16_t)(an[i] & 0xffffu), c1 = (uint16_t)(an[i] >> 16);
+                    const float prev0 = tk[2 * i] >= 0 ? elem_to_float<BF16>(pt[(2 * i) * QROWS]) : 0.f;
+                    const float prev1 = tk[2 * i + 1] >= 0 ? elem_to_float<BF16>(pt[(2 * i + 1) * QROWS]) : 0.f;
+                    // dA = a_n - p (modules.py:196), p[:, idx] = a_n (modules.py:200)
+                    ad[i] = float_to_elem<BF16>(elem_to_float<BF16>(c0) - prev0) |
+                            (float_to_elem<BF16>(elem_to_float<BF16>(c1) - prev1) << 16);
+                    pt[(2 * i) * QROWS] = c0;
+                    pt[(2 * i + 1) * QROWS] = c1;
                 }
             } else if (MODE == ET_ATTN_FIRST) {
-                uint16_t* pt = Pt(u) + row;
+                uint16_t* pt = Pt(u) + (half * 32) * QROWS + row;
 #pragma unroll
-                for (int j = 0; j < 64; ++j) pt[j * QROWS] = (uint16_t)((an[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
-            }
-            if (t >= 2) mbar_wait(smem_u32(&pv_done[u]), ph ^ 1);  // the P tiles of tile t-2 have been consumed
-            // P tiles as K-major, 128-byte-swizzled A operands: row r, 16-byte chunk c -> c ^ (r % 8)
-            {
-                uint8_t* pn_row = Pn(u) + (row >> 3) * 1024 + (row & 7) * 128;
-                uint8_t* pd_row = Pd(u) + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int sw = (c ^ (row & 7)) * 16;
-                    *reinterpret_cast<uint4*>(pn_row + sw) = make_uint4(an[c * 4], an[c * 4 + 1], an[c * 4 + 2], an[c * 4 + 3]);
-                    if (MODE == ET_ATTN_DELTA)
-                        *reinterpret_cast<uint4*>(pd_row + sw) = make_uint4(ad[c * 4], ad[c * 4 + 1], ad[c * 4 + 2], ad[c * 4 + 3]);
+                for (int i = 0; i < 16; ++i) {
+                    pt[(2 * i) * QROWS] = (uint16_t)(an[i] & 0xffffu);
+                    pt[(2 * i + 1) * QROWS] = (uint16_t)(an[i] >> 16);
                 }
             }
-            fence_proxy_async();  // generic-proxy smem writes -> visible to tcgen05.mma and the bulk stores
+            if (t >= 1) mbar_wait(smem_u32(&pv_done[(t - 1) & 1]), ((t - 1) >> 1) & 1);  // single P buffer: tile t-1 consumed
+            // P tiles as K-major, 128-byte-swizzled A operands: row r, 16-byte chunk c -> c ^ (r % 8)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int sw = ((half * 4 + c) ^ (row & 7)) * 16;
+                *reinterpret_cast<uint4*>(pn_row + sw) = make_uint4(an[c * 4], an[c * 4 + 1], an[c * 4 + 2], an[c * 4 + 3]);
+                if (MODE == ET_ATTN_DELTA)
+                    *reinterpret_cast<uint4*>(pd_row + sw) = make_uint4(ad[c * 4], ad[c * 4 + 1], ad[c * 4 + 2], ad[c * 4 + 3]);
+            }
+            fence_proxy_async();  // generic-proxy smem writes -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(smem_u32(&p_ready[u]));
+                mbar_arrive(smem_u32(p_ready));
                 if (MODE != ET_ATTN_DENSE) mbar_arrive(smem_u32(&ps_done[u]));
             }
         }
-        // ---- epilogue: acc += O, out = acc
+        // ---- epilogue: acc += O, out = acc ; each thread writes its row's 32 of the head's 64 output columns
         uint16_t* acc = static_cast<uint16_t*>(a.acc);
         uint16_t* out = static_cast<uint16_t*>(a.out);
-        const size_t off = ((size_t)b * a.N + q0 + row) * a.D + h * 64;
-        float o[64];
+        const size_t off = ((size_t)b * a.N + q0 + row) * a.D + h * 64 + half * 32;
+        uint32_t o[32];
         if (T > 0) {
             mbar_wait(smem_u32(o_full), 0);
             tcgen05_fence_after();
-            uint32_t lo[32], hi[32];
-            tmem_load_32x32(taddr + (uint32_t)(2 * AP_KEYS), lo);
-            tmem_load_32x32(taddr + (uint32_t)(2 * AP_KEYS + 32), hi);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                o[i] = __uint_as_float(lo[i]);
-                o[32 + i] = __uint_as_float(hi[i]);
-            }
+            tmem_load_32x32(taddr + (uint32_t)(2 * AP_KEYS + half * 32), o);
         } else {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) o[i] = 0.f;
+            for (int i = 0; i < 32; ++i) o[i] = 0u;
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
             uint32_t w[4];
             uint4 prev = make_uint4(0, 0, 0, 0);
             if (MODE == ET_ATTN_DELTA) prev = *reinterpret_cast<const uint4*>(acc + off + c * 8);
             const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                float lo = o[c * 8 + 2 * i], hi = o[c * 8 + 2 * i + 1];
+                float lo = __uint_as_float(o[c * 8 + 2 * i]), hi = __uint_as_float(o[c * 8 + 2 * i + 1]);
                 if (MODE == ET_ATTN_DELTA) {
                     lo += elem_to_float<BF16>((uint16_t)(pw[i] & 0xffffu));
                     hi += elem_to_float<BF16>((uint16_t)(pw[i] >> 16));
                 }
-                w[i] = (uint32_t)float_to_elem<BF16>(lo) | ((uint32_t)float_to_elem<BF16>(hi) << 16);
+                w[i] = float_to_elem<BF16>(lo) | (float_to_elem<BF16>(hi) << 16);
             }
             const uint4 pk = make_uint4(w[0], w[1], w[2], w[3]);
             if (MODE != ET_ATTN_DENSE) *reinterpret_cast<uint4*>(acc + off + c * 8) = pk;
@@ -507,6 +516,22 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
 }
 
+// One-hot key coordinates for the augmented K operand: row j = [onehot(ky_j) (64) | onehot(kx_j) (64)].
+template <bool BF16>
+__global__ void __launch_bounds__(256) onehot_kernel(const long long* idx, uint16_t* oh, int rows, int gw) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk (8 columns) per thread
+    if (g >= rows * 16) return;
+    const int j = g >> 4, chunk = g & 15;
+    const int tok = idx != nullptr ? (int)idx[j] : j;
+    const int ky = tok / gw, kx = tok - ky * gw;
+    const int hot = chunk < 8 ? ky : 64 + kx;
+    const uint32_t one = float_to_elem<BF16>(1.f);
+    uint32_t w[4] = {0, 0, 0, 0};
+    const int base = chunk * 8;
+    if (hot >= base && hot < base + 8) w[(hot - base) >> 1] = one << (((hot - base) & 1) * 16);
+    *reinterpret_cast<uint4*>(oh + (size_t)j * 128 + base) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <typename K>
 int raise_smem(K kernel, int bytes) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -515,7 +540,7 @@ int raise_smem(K kernel, int bytes) {
 }
 
 template <bool BF16>
-int launch_tc(const void* qkv, const void* sel, const TcArgs& a, int mode, cudaStream_t s) {
+int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, int mode, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         int rc;
@@ -525,20 +550,31 @@ int launch_tc(const void* qkv, const void* sel, const TcArgs& a, int mode, cudaS
         if ((rc = raise_smem(tc_apply_kernel<BF16, ET_ATTN_DELTA>, AP_SMEM))) return rc;
         configured = true;
     }
-    CUtensorMap tm128, tm64, tmsel;
+    CUtensorMap tm128, tm64, tmsel, tmbh, tmbw, tmoh;
     int rc;
     if ((rc = make_tmap_2d(&tm128, qkv, (long long)a.B * a.N, 3LL * a.D, 128, a.is_bf16))) return rc;
     if ((rc = make_tmap_2d(&tm64, qkv, (long long)a.B * a.N, 3LL * a.D, 64, a.is_bf16))) return rc;
+    tmbh = tmbw = tmoh = tm128;  // placeholders when there is no rel-pos bias (never dereferenced)
+    const int oh_rows = mode == ET_ATTN_DELTA ? a.B * a.k : a.N;
+    if (a.has_bias) {
+        const long long brows = (long long)a.B * a.H * a.N;
+        if ((rc = make_tmap_2d(&tmbh, a.bias_h, brows, 64, 128, a.is_bf16))) return rc;
+        if ((rc = make_tmap_2d(&tmbw, a.bias_w, brows, 64, 128, a.is_bf16))) return rc;
+        if ((rc = make_tmap_2d(&tmoh, onehot, oh_rows, 128, 64, a.is_bf16))) return rc;
+        onehot_kernel<BF16><<<(oh_rows * 16 + 255) / 256, 256, 0, s>>>(mode == ET_ATTN_DELTA ? a.idx : nullptr,
+                                                                        static_cast<uint16_t*>(onehot), oh_rows, a.gw);
+        ET_COUNT_LAUNCH(1);
+    }
     const dim3 grid(a.N / QROWS, a.H, a.B);
     tc_stats_kernel<BF16><<<grid, kThreads, ST_SMEM, s>>>(tm128, a);
     ET_COUNT_LAUNCH(1);
     if (mode == ET_ATTN_DELTA) {
         if ((rc = make_tmap_2d(&tmsel, sel, 3LL * a.sel_rows, (long long)a.D, 64, a.is_bf16))) return rc;
-        tc_apply_kernel<BF16, ET_ATTN_DELTA><<<grid, kThreads, AP_SMEM, s>>>(tm128, tmsel, a);
+        tc_apply_kernel<BF16, ET_ATTN_DELTA><<<grid, kThreads, AP_SMEM, s>>>(tm128, tmsel, tmbh, tmbw, tmoh, a);
     } else if (mode == ET_ATTN_FIRST) {
-        tc_apply_kernel<BF16, ET_ATTN_FIRST><<<grid, kThreads, AP_SMEM, s>>>(tm128, tm64, a);
+        tc_apply_kernel<BF16, ET_ATTN_FIRST><<<grid, kThreads, AP_SMEM, s>>>(tm128, tm64, tmbh, tmbw, tmoh, a);
     } else {
-        tc_apply_kernel<BF16, ET_ATTN_DENSE><<<grid, kThreads, AP_SMEM, s>>>(tm128, tm64, a);
+        tc_apply_kernel<BF16, ET_ATTN_DENSE><<<grid, kThreads, AP_SMEM, s>>>(tm128, tm64, tmbh, tmbw, tmoh, a);
     }
     ET_COUNT_LAUNCH(1);
     return ET_OK;
@@ -547,14 +583,16 @@ int launch_tc(const void* qkv, const void* sel, const TcArgs& a, int mode, cudaS
 }  // namespace
 
 // Entry used by et_global_attention (et_attn.cu) when the shape qualifies for the tensor-core path.
-// `sel` = workspace rows [K_sel | dV | v_n - dV], each (B * k, D); bias tables as produced by relpos_bias_kernel.
-int et_tc_global_attention(const void* qkv, const void* sel, const void* bias_h, const void* bias_w, int mode,
+// `sel` = workspace rows [K_sel | dV | v_n - dV], each (B * k, D); `onehot` = (max(B * k, N), 128) scratch;
+// bias tables in the tc layout: (B, H, N, 64) each, holding 8 x bias, zero padded.
+int et_tc_global_attention(const void* qkv, const void* sel, void* onehot, const void* bias_h, const void* bias_w, int mode,
                            const long long* idx, int k, void* a_state, void* acc, void* out, float* stats, int B, int N,
                            int NP, int H, int gh, int gw, int is_bf16, cudaStream_t stream) {
     TcArgs a;
     a.bias_h = bias_h; a.bias_w = bias_w; a.stats = stats; a.idx = idx; a.a_state = a_state; a.acc = acc; a.out = out;
     a.B = B; a.N = N; a.NP = NP; a.H = H; a.D = H * 64; a.gh = gh; a.gw = gw; a.k = k; a.is_bf16 = is_bf16;
     a.sel_rows = B * k;
+    a.has_bias = bias_h != nullptr;
     a.c1 = 0.125f * kLog2e;
-    return is_bf16 ? launch_tc<true>(qkv, sel, a, mode, stream) : launch_tc<false>(qkv, sel, a, mode, stream);
+    return is_bf16 ? launch_tc<true>(qkv, sel, onehot, a, mode, stream) : launch_tc<false>(qkv, sel, onehot, a, mode, stream);
 }

@@ -32,7 +32,7 @@ struct GateArgs {
     int* count;
     int* ticket;
     int tokens_per_cta;
-    int passes;
+    int low_bit;  // lowest significant bit of the fp32 key for this dtype
 };
 
 // Order-preserving key of a float (torch's radix-select convention: NaN sorts largest).
@@ -108,11 +108,10 @@ __device__ __forceinline__ void layer_norm_row(float (&v)[CPL * ElemTraits<T>::V
 // ------------------------------------------------------------------------------------------
 // Selection stage, executed by one CTA per row after all norms of the row are visible.
 // ------------------------------------------------------------------------------------------
-__device__ void select_row(const GateArgs& a, int r, uint32_t* s_keys, int* s_hist, int* s_whist, int* s_misc) {
+__device__ void select_row(const GateArgs& a, int r, int* s_hist) {
     const int tid = threadIdx.x;
     const int N = a.N;
     const float* norm = a.norm + (size_t)r * N;
-    const bool in_smem = N <= kSmemKeys;
     long long* out = a.idx + (size_t)r * (a.mode == ET_SELECT_TOPK ? a.k : N);
     const int per = (N + kGateThreads - 1) / kGateThreads;
     const int lo = min(N, tid * per), hi = min(N, lo + per);
@@ -140,76 +139,57 @@ __device__ void select_row(const GateArgs& a, int r, uint32_t* s_keys, int* s_hi
     }
 
     if (a.k == 0) return;
-    if (in_smem)
-        for (int i = tid; i < N; i += kGateThreads) s_keys[i] = order_key(__ldcg(norm + i));
-    auto key_at = [&](int i) -> uint32_t { return in_smem ? s_keys[i] : order_key(__ldcg(norm + i)); };
-
-    uint32_t prefix = 0, mask = 0;
-    int remaining = a.k;
-    for (int pass = 0; pass < a.passes; ++pass) {
-        const int shift = 24 - 8 * pass;
-        // per-warp histograms with warp-aggregated increments: norms cluster in a handful of digit bins,
-        // so plain shared atomics would serialise the whole CTA on one bank
+    // ---- k-th largest key by bitwise binary search (no atomics, no histograms): thread t keeps the keys of
+    // tokens [t * per, (t + 1) * per) in registers; every step counts the keys >= candidate with one REDUX per
+    // warp and one barrier.  Steps = significant key bits (16 for bf16, 19 for fp16, 32 for fp32 norms).
+    constexpr int KPT = kSmemKeys / kGateThreads;  // register-resident keys per thread (N <= 8192)
+    uint32_t keys[KPT];
+    const bool in_regs = per <= KPT;
+    if (in_regs) {
 #pragma unroll
-        for (int w = 0; w < kGateThreads / 32; ++w) s_whist[w * 256 + tid] = 0;
-        __syncthreads();
-        for (int base = 0; base < N; base += kGateThreads) {
-            const int i = base + tid;
-            const uint32_t key = i < N ? key_at(i) : 0u;
-            const bool on = i < N && (key & mask) == prefix;
-            const unsigned active = __ballot_sync(0xffffffffu, on);
-            if (on) {
-                const uint32_t bin = (key >> shift) & 0xffu;
-                const unsigned peers = __match_any_sync(active, bin);
-                if (lane == __ffs(peers) - 1) s_whist[warp * 256 + bin] += __popc(peers);
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-        {
-            int total = 0;
-#pragma unroll
-            for (int w = 0; w < kGateThreads / 32; ++w) total += s_whist[w * 256 + tid];
-            s_hist[tid] = total;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            int total = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) total += s_hist[lane * 8 + j];
-            int suf = total;  // inclusive suffix sum over lanes (high digits first)
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_down_sync(0xffffffffu, suf, o);
-                if (lane + o < 32) suf += t;
-            }
-            const int above = suf - total;
-            if (above < remaining && remaining <= suf) {
-                int run = above;
-                for (int j = 7; j >= 0; --j) {
-                    const int c = s_hist[lane * 8 + j];
-                    if (run + c >= remaining) {
-                        s_misc[0] = lane * 8 + j;
-                        s_misc[1] = remaining - run;
-                        break;
-                    }
-                    run += c;
-                }
-            }
-        }
-        __syncthreads();
-        prefix |= (uint32_t)s_misc[0] << shift;
-        mask |= 0xffu << shift;
-        remaining = s_misc[1];
-        __syncthreads();
+        for (int j = 0; j < KPT; ++j) keys[j] = (lo + j < hi) ? order_key(__ldcg(norm + lo + j)) : 0u;
     }
-    // prefix = (masked) key of the k-th largest norm; `remaining` of the equal keys are taken.
-    const int n_greater = a.k - remaining;
+    auto count_ge = [&](uint32_t cand) -> int {
+        int c = 0;
+        if (in_regs) {
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) c += (lo + j < hi) && keys[j] >= cand;
+        } else {
+            for (int i = lo; i < hi; ++i) c += order_key(__ldcg(norm + i)) >= cand;
+        }
+        return c;
+    };
+    auto block_sum = [&](int v, int slot) -> int {  // slot alternates so one barrier per step is enough
+        const int w = __reduce_add_sync(0xffffffffu, v);
+        if (lane == 0) s_hist[slot * 8 + warp] = w;
+        __syncthreads();
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < kGateThreads / 32; ++i) tot += s_hist[slot * 8 + i];
+        return tot;
+    };
+    uint32_t kth = 0;
+    for (int bit = 31; bit >= a.low_bit; --bit) {
+        const uint32_t cand = kth | (1u << bit);
+        if (block_sum(count_ge(cand), bit & 3) >= a.k) kth = cand;
+    }
+    // kth = k-th largest key (low insignificant bits zero). Strictly greater keys first (ascending index), then
+    // keys equal to it (ascending index) until k are written: torch's CUDA radix-select order.
+    const uint32_t mask = a.low_bit == 0 ? 0xffffffffu : ~((1u << a.low_bit) - 1u);
     int cg = 0, ce = 0;
-    for (int i = lo; i < hi; ++i) {
-        const uint32_t key = key_at(i) & mask;
-        cg += key > prefix;
-        ce += key == prefix;
+    if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) {
+            const bool on = lo + j < hi;
+            cg += on && (keys[j] & mask) > kth;
+            ce += on && (keys[j] & mask) == kth;
+        }
+    } else {
+        for (int i = lo; i < hi; ++i) {
+            const uint32_t key = order_key(__ldcg(norm + i)) & mask;
+            cg += key > kth;
+            ce += key == kth;
+        }
     }
     int ig = cg, ie = ce;
 #pragma unroll
@@ -221,22 +201,30 @@ __device__ void select_row(const GateArgs& a, int r, uint32_t* s_keys, int* s_hi
             ie += te;
         }
     }
+    __syncthreads();
     if (lane == 31) {
-        s_hist[warp] = ig;
-        s_hist[32 + warp] = ie;
+        s_hist[64 + warp] = ig;
+        s_hist[96 + warp] = ie;
     }
     __syncthreads();
-    int bg = 0, be = 0;
-    for (int w = 0; w < warp; ++w) {
-        bg += s_hist[w];
-        be += s_hist[32 + w];
+    int bg = 0, be = 0, n_greater = 0;
+#pragma unroll
+    for (int w = 0; w < kGateThreads / 32; ++w) {
+        if (w < warp) {
+            bg += s_hist[64 + w];
+            be += s_hist[96 + w];
+        }
+        n_greater += s_hist[64 + w];
     }
+    const int remaining = a.k - n_greater;
     int pg = bg + ig - cg, pe = be + ie - ce;
-    for (int i = lo; i < hi; ++i) {
-        const uint32_t key = key_at(i) & mask;
-        if (key > prefix) {
+    for (int j = 0; j < (in_regs ? KPT : per); ++j) {
+        const int i = lo + j;
+        if (i >= hi) break;
+        const uint32_t key = (in_regs ? keys[j] : order_key(__ldcg(norm + i))) & mask;
+        if (key > kth) {
             out[pg++] = i;
-        } else if (key == prefix) {
+        } else if (key == kth) {
             if (pe < remaining) out[n_greater + pe] = i;
             ++pe;
         }
@@ -247,9 +235,7 @@ template <typename T, int LPT, int CPL>
 __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArgs a) {
     constexpr int VEC = ElemTraits<T>::VEC;
     constexpr int GROUPS = kGateThreads / LPT;
-    __shared__ uint32_t s_keys[kSmemKeys];
-    __shared__ int s_hist[256];
-    __shared__ int s_whist[(kGateThreads / 32) * 256];
+    __shared__ int s_hist[128];
     __shared__ int s_misc[4];
 
     const int r = blockIdx.y;
@@ -308,7 +294,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
     __syncthreads();
     if (!s_misc[2]) return;
     __threadfence();
-    select_row(a, r, s_keys, s_hist, s_whist, s_misc);
+    select_row(a, r, s_hist);
     if (threadIdx.x == 0) a.ticket[r] = 0;  // self-reset so the workspace is reusable / graph-replayable
 }
 
@@ -593,7 +579,7 @@ int et_gate_select(const void* xa, const void* xb, void* xsum_out, const void* l
         long long ctas = want < 1 ? 1 : (want > max_ctas ? max_ctas : want);
         a.tokens_per_cta = (int)((N + ctas - 1) / ctas);
         ctas = (N + a.tokens_per_cta - 1) / a.tokens_per_cta;
-        a.passes = sizeof(T) == 4 ? 4 : (dtype == ET_BF16 ? 2 : 3);
+        a.low_bit = sizeof(T) == 4 ? 0 : (dtype == ET_BF16 ? 16 : 13);
         a.thr = (dtype == ET_F32) ? threshold
                                   : (dtype == ET_BF16 ? __bfloat162float(__float2bfloat16_rn(threshold))
                                                       : __half2float(__float2half_rn(threshold)));

@@ -111,6 +111,20 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// 16-byte cp.async (LDGSTS) and its mbarrier completion: each participating thread's prior cp.asyncs arrive
+// on the barrier when they land (the barrier's expected count includes one arrival per participating thread)
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // MN-major operand tile (rows = K index, 128-byte rows of 64 contiguous MN elements), 128-byte swizzle:
 // 8-row groups 1024 bytes apart (SBO); a single 64-element MN block, so LBO is unused.
 __device__ __forceinline__ uint64_t umma_smem_desc_mn(uint32_t smem_addr) { return umma_smem_desc(smem_addr); }
