@@ -228,7 +228,8 @@ constexpr int AP_PT = AP_KEYS * QROWS * 2;        // 16 KB: a_state tile [key][r
 constexpr int AP_P = QROWS * AP_KEYS * 2;         // 16 KB: P tile (A operand)
 constexpr int AP_OFF_ST = 3 * QROWS * 128;        // Q' = three 16 KB blocks: q, 8 bias_h, 8 bias_w
 constexpr int AP_OFF_PT = AP_OFF_ST + 2 * AP_STAGE;
-constexpr int AP_OFF_P = AP_OFF_PT + 2 * AP_PT;
+constexpr int AP_PT_STAGES = 3;                   // a_state tiles are prefetched three tiles ahead by the softmax threads
+constexpr int AP_OFF_P = AP_OFF_PT + AP_PT_STAGES * AP_PT;
 constexpr int AP_OFF_MISC = AP_OFF_P + 2 * AP_P;
 constexpr int AP_SMEM = AP_OFF_MISC + 1024 + 1024;
 
@@ -250,14 +251,13 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AP_OFF_MISC + 512);
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;
-    uint64_t* ps_full = bars + 3;
-    uint64_t* s_full = bars + 5;
-    uint64_t* s_empty = bars + 7;
-    uint64_t* p_ready = bars + 9;   // single P buffer: one barrier, one phase per tile
-    uint64_t* pv_done = bars + 10;  // [2]: PV MMAs of tile t commit to slot t & 1 (at most one phase outstanding each)
-    uint64_t* ps_done = bars + 12;  // [2]
-    uint64_t* o_full = bars + 14;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* ps_full = bars + 3;   // [3]: a_state tile landed (256 cp.async arrivals, one per softmax thread)
+    uint64_t* s_full = bars + 6;
+    uint64_t* s_empty = bars + 8;
+    uint64_t* p_ready = bars + 10;  // single P buffer: one barrier, one phase per tile
+    uint64_t* pv_done = bars + 11;  // [2]: PV MMAs of tile t commit to slot t & 1 (at most one phase outstanding each)
+    uint64_t* o_full = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * QROWS, h = blockIdx.y, b = blockIdx.z;
@@ -275,12 +275,11 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_init(smem_u32(p_ready), 8);
         for (int u = 0; u < 2; ++u) {
             mbar_init(smem_u32(&kv_full[u]), 1);
-            mbar_init(smem_u32(&ps_full[u]), 32);  // one cp.async arrival per producer lane
             mbar_init(smem_u32(&s_full[u]), 1);
             mbar_init(smem_u32(&s_empty[u]), 8);
-            mbar_init(smem_u32(&ps_done[u]), 8);
             mbar_init(smem_u32(&pv_done[u]), 1);
         }
+        for (int u = 0; u < AP_PT_STAGES; ++u) mbar_init(smem_u32(&ps_full[u]), 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
@@ -302,20 +301,6 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tma_load_2d(smem_u32(Qb(2)), &tm_bw, smem_u32(q_full), 0, brow);
             }
         }
-        // one selected column x this CTA's 128 rows = 256 contiguous bytes = 16 lanes x 16 B: two columns per warp op
-        const int sub = lane >> 4, seg = (lane & 15) * 8;
-        auto write_back = [&](int tt) {  // a_state[:, idx of tile tt] <- a_n (softmax warps left it in Pt)
-            const int u = tt & 1;
-            mbar_wait(smem_u32(&ps_done[u]), (tt >> 1) & 1);
-#pragma unroll 8
-            for (int i = 0; i < AP_KEYS / 2; ++i) {
-                const int j = 2 * i + sub;
-                const int tok = s_tok[u * AP_KEYS + j];
-                if (tok >= 0)
-                    *reinterpret_cast<uint4*>(a_state + a_head + (size_t)tok * a.NP + q0 + seg) =
-                        *reinterpret_cast<const uint4*>(Pt(u) + j * QROWS + seg);
-            }
-        };
         for (int t = 0; t < T; ++t) {
             const int u = t & 1, key0 = t * AP_KEYS;
             if (t >= 2) mbar_wait(smem_u32(&pv_done[u]), ((t >> 1) & 1) ^ 1);  // tile t-2: the MMAs are done with slot u
@@ -346,19 +331,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     tma_load_2d(smem_u32(Kb(u, 2)), &tm_oh, fb, 64, orow);
                 }
             }
-            if (MODE == ET_ATTN_DELTA) {  // previous attention values of the selected columns -> smem tile [key][row]
-#pragma unroll 8
-                for (int i = 0; i < AP_KEYS / 2; ++i) {
-                    const int j = 2 * i + sub;
-                    const int tj = s_tok[u * AP_KEYS + j];
-                    if (tj >= 0)
-                        cp_async_16(smem_u32(Pt(u) + j * QROWS + seg), a_state + a_head + (size_t)tj * a.NP + q0 + seg);
-                }
-                cp_async_arrive_noinc(smem_u32(&ps_full[u]));
-            }
-            if (MODE != ET_ATTN_DENSE && t >= 1) write_back(t - 1);
         }
-        if (MODE != ET_ATTN_DENSE && T >= 1) write_back(T - 1);
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
@@ -416,6 +389,37 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         uint8_t* pn_row = Pn + (row >> 3) * 1024 + (row & 7) * 128;
         uint8_t* pd_row = Pd + (row >> 3) * 1024 + (row & 7) * 128;
+        // A-gate state traffic is spread over the 256 softmax threads: a selected column x this CTA's 128 rows is 256
+        // contiguous bytes = 16 threads x 16 B; thread st moves segment (st & 15) of columns (st >> 4) + 16 i, i < 4.
+        const int st = threadIdx.x - 64;
+        const int seg = (st & 15) * 8, col0 = st >> 4;
+        auto tile_tok = [&](int tt, int i) -> int {  // token of column col0 + 16 i of tile tt (or -1)
+            const int j = tt * AP_KEYS + col0 + 16 * i;
+            if (j >= nkeys) return -1;
+            return (MODE == ET_ATTN_DELTA) ? (int)a.idx[(size_t)b * a.k + j] : j;
+        };
+        auto load_state = [&](int tt, const int (&tok)[4]) {  // a_state[:, idx of tile tt] -> Pt ring
+            uint16_t* dst = Pt(tt % AP_PT_STAGES);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (tok[i] >= 0)
+                    cp_async_16(smem_u32(dst + (col0 + 16 * i) * QROWS + seg),
+                                a_state + a_head + (size_t)tok[i] * a.NP + q0 + seg);
+            cp_async_arrive_noinc(smem_u32(&ps_full[tt % AP_PT_STAGES]));
+        };
+        int tok_next[4] = {-1, -1, -1, -1};  // tokens of the tile AP_PT_STAGES ahead (index loads issued a tile early)
+        if (MODE == ET_ATTN_DELTA) {
+            for (int tt = 0; tt < AP_PT_STAGES && tt < T; ++tt) {
+                int tk0[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tk0[i] = tile_tok(tt, i);
+                load_state(tt, tk0);
+            }
+            if (AP_PT_STAGES < T) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tok_next[i] = tile_tok(AP_PT_STAGES, i);
+            }
+        }
         for (int t = 0; t < T; ++t) {
             const int u = t & 1;
             const uint32_t ph = (t >> 1) & 1;
@@ -437,9 +441,10 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const uint32_t e1 = tk[2 * i + 1] >= 0 ? float_to_elem<BF16>(p1) : 0u;
                 an[i] = e0 | (e1 << 16);
             }
+            const int ps = t % AP_PT_STAGES;
             if (MODE == ET_ATTN_DELTA) {
-                mbar_wait(smem_u32(&ps_full[u]), ph);
-                uint16_t* pt = Pt(u) + (half * 32) * QROWS + row;
+                mbar_wait(smem_u32(&ps_full[ps]), (t / AP_PT_STAGES) & 1);
+                uint16_t* pt = Pt(ps) + (half * 32) * QROWS + row;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const uint16_t c0 = (uint16_t)(an[i] & 0xffffu), c1 = (uint16_t)(an[i] >> 16);
@@ -452,7 +457,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     pt[(2 * i + 1) * QROWS] = c1;
                 }
             } else if (MODE == ET_ATTN_FIRST) {
-                uint16_t* pt = Pt(u) + (half * 32) * QROWS + row;
+                uint16_t* pt = Pt(ps) + (half * 32) * QROWS + row;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     pt[(2 * i) * QROWS] = (uint16_t)(an[i] & 0xffffu);
@@ -470,9 +475,29 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             fence_proxy_async();  // generic-proxy smem writes -> visible to tcgen05.mma
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(smem_u32(p_ready));
-                if (MODE != ET_ATTN_DENSE) mbar_arrive(smem_u32(&ps_done[u]));
+            if (lane == 0) mbar_arrive(smem_u32(p_ready));
+            if (MODE != ET_ATTN_DENSE) {
+                // write the updated columns back (a_state[:, idx] = a_n) and refill the ring slot three tiles ahead
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // every row of the tile is in Pt(ps)
+                uint4 wb[4];
+                int tk_wb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    tk_wb[i] = s_tok[u * AP_KEYS + col0 + 16 * i];
+                    wb[i] = *reinterpret_cast<const uint4*>(Pt(ps) + (col0 + 16 * i) * QROWS + seg);
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");  // all reads of the slot done: it may be refilled
+                if (MODE == ET_ATTN_DELTA && t + AP_PT_STAGES < T) {
+                    load_state(t + AP_PT_STAGES, tok_next);
+                    if (t + AP_PT_STAGES + 1 < T) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tok_next[i] = tile_tok(t + AP_PT_STAGES + 1, i);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (tk_wb[i] >= 0)
+                        *reinterpret_cast<uint4*>(a_state + a_head + (size_t)tk_wb[i] * a.NP + q0 + seg) = wb[i];
             }
         }
         // ---- epilogue: acc += O, out = acc ; each thread writes its row's 32 of the head's 64 output columns

@@ -12,6 +12,8 @@
 thread_local char g_et_error[512] = "";
 long long g_et_launches = 0;
 
+unsigned long long* g_gate_dbg = nullptr;  // et_debug_set(3, device pointer to 8 x u64) enables phase timestamps
+
 namespace {
 
 constexpr int kGateThreads = 256;
@@ -33,7 +35,14 @@ struct GateArgs {
     int* ticket;
     int tokens_per_cta;
     int low_bit;  // lowest significant bit of the fp32 key for this dtype
+    unsigned long long* dbg;  // optional phase timestamps (et_debug_set key 3)
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // Order-preserving key of a float (torch's radix-select convention: NaN sorts largest).
 __device__ __forceinline__ uint32_t order_key(float v) {
@@ -71,6 +80,7 @@ __device__ __forceinline__ void load_row(const T* xa, const T* xb, T* xsum, size
 }
 
 // In-register LayerNorm over one row spread across LPT lanes (two-pass, fp32), result rounded to T.
+// w / b may point to shared memory (gate_select stages them once per CTA) or global memory (gate_gather).
 template <typename T, int LPT, int CPL>
 __device__ __forceinline__ void layer_norm_row(float (&v)[CPL * ElemTraits<T>::VEC], const T* w, const T* b,
                                                int nchunks, int lane, int D, float eps) {
@@ -108,7 +118,8 @@ __device__ __forceinline__ void layer_norm_row(float (&v)[CPL * ElemTraits<T>::V
 // ------------------------------------------------------------------------------------------
 // Selection stage, executed by one CTA per row after all norms of the row are visible.
 // ------------------------------------------------------------------------------------------
-__device__ void select_row(const GateArgs& a, int r, int* s_hist) {
+template <int KPT>  // register-resident key slots per thread (N <= KPT * 256)
+__device__ __forceinline__ void select_row(const GateArgs& a, int r, int* s_hist, uint32_t* s_keys) {
     const int tid = threadIdx.x;
     const int N = a.N;
     const float* norm = a.norm + (size_t)r * N;
@@ -139,40 +150,67 @@ __device__ void select_row(const GateArgs& a, int r, int* s_hist) {
     }
 
     if (a.k == 0) return;
-    // ---- k-th largest key by bitwise binary search (no atomics, no histograms): thread t keeps the keys of
-    // tokens [t * per, (t + 1) * per) in registers; every step counts the keys >= candidate with one REDUX per
-    // warp and one barrier.  Steps = significant key bits (16 for bf16, 19 for fp16, 32 for fp32 norms).
-    constexpr int KPT = kSmemKeys / kGateThreads;  // register-resident keys per thread (N <= 8192)
+    // ---- k-th largest key by radix search on 2-bit digits, no atomics: thread t keeps the keys of tokens
+    // [t * per, (t + 1) * per) in registers (coalesced 128-bit loads staged through shared memory); per step every
+    // thread tallies its candidate keys into one 64-bit word of four 16-bit counters, two REDUX sum a warp and one
+    // barrier sums the CTA.  Steps = ceil(significant key bits / 2): 8 for bf16, 10 for fp16, 16 for fp32 norms.
     uint32_t keys[KPT];
     const bool in_regs = per <= KPT;
     if (in_regs) {
+        if ((N & 3) == 0) {
+            const float4* n4 = reinterpret_cast<const float4*>(norm);
+            for (int i = tid; i < N / 4; i += kGateThreads) {
+                const float4 f = __ldcg(n4 + i);
+                *reinterpret_cast<uint4*>(s_keys + 4 * i) = make_uint4(order_key(f.x), order_key(f.y), order_key(f.z), order_key(f.w));
+            }
+        } else {
+            for (int i = tid; i < N; i += kGateThreads) s_keys[i] = order_key(__ldcg(norm + i));
+        }
+        __syncthreads();
 #pragma unroll
-        for (int j = 0; j < KPT; ++j) keys[j] = (lo + j < hi) ? order_key(__ldcg(norm + lo + j)) : 0u;
+        for (int j = 0; j < KPT; ++j) keys[j] = (lo + j < hi) ? s_keys[lo + j] : 0u;
     }
-    auto count_ge = [&](uint32_t cand) -> int {
-        int c = 0;
+    if (a.dbg != nullptr && tid == 0) a.dbg[3] = gtime();
+    uint32_t kth = 0, known = 0;  // `known` = mask of the key bits decided so far
+    int remaining = a.k;
+    int slot = 0;
+    for (int shift = 30; shift + 1 >= a.low_bit; shift -= 2, slot ^= 1) {
+        unsigned long long cnt = 0;  // four 16-bit counters: digit d in bits [16 d, 16 d + 16)
         if (in_regs) {
 #pragma unroll
-            for (int j = 0; j < KPT; ++j) c += (lo + j < hi) && keys[j] >= cand;
+            for (int j = 0; j < KPT; ++j)
+                if (lo + j < hi && (keys[j] & known) == kth) cnt += 1ull << (((keys[j] >> shift) & 3u) * 16);
         } else {
-            for (int i = lo; i < hi; ++i) c += order_key(__ldcg(norm + i)) >= cand;
+            for (int i = lo; i < hi; ++i) {
+                const uint32_t key = order_key(__ldcg(norm + i));
+                if ((key & known) == kth) cnt += 1ull << (((key >> shift) & 3u) * 16);
+            }
         }
-        return c;
-    };
-    auto block_sum = [&](int v, int slot) -> int {  // slot alternates so one barrier per step is enough
-        const int w = __reduce_add_sync(0xffffffffu, v);
-        if (lane == 0) s_hist[slot * 8 + warp] = w;
+        const uint32_t lo32 = __reduce_add_sync(0xffffffffu, (uint32_t)cnt);
+        const uint32_t hi32 = __reduce_add_sync(0xffffffffu, (uint32_t)(cnt >> 32));
+        if (lane == 0) {
+            s_hist[slot * 16 + warp * 2] = (int)lo32;
+            s_hist[slot * 16 + warp * 2 + 1] = (int)hi32;
+        }
         __syncthreads();
-        int tot = 0;
+        uint32_t t01 = 0, t23 = 0;
 #pragma unroll
-        for (int i = 0; i < kGateThreads / 32; ++i) tot += s_hist[slot * 8 + i];
-        return tot;
-    };
-    uint32_t kth = 0;
-    for (int bit = 31; bit >= a.low_bit; --bit) {
-        const uint32_t cand = kth | (1u << bit);
-        if (block_sum(count_ge(cand), bit & 3) >= a.k) kth = cand;
+        for (int q = 0; q < kGateThreads / 32; ++q) {
+            t01 += (uint32_t)s_hist[slot * 16 + q * 2];
+            t23 += (uint32_t)s_hist[slot * 16 + q * 2 + 1];
+        }
+        const int c3 = (int)(t23 >> 16), c2 = (int)(t23 & 0xffffu), c1 = (int)(t01 >> 16);
+        int digit, above;  // the digit whose suffix count (from the top) reaches `remaining`
+        if (c3 >= remaining) { digit = 3; above = 0; }
+        else if (c3 + c2 >= remaining) { digit = 2; above = c3; }
+        else if (c3 + c2 + c1 >= remaining) { digit = 1; above = c3 + c2; }
+        else { digit = 0; above = c3 + c2 + c1; }
+        kth |= (uint32_t)digit << shift;
+        known |= 3u << shift;
+        remaining -= above;
     }
+    kth &= (a.low_bit == 0 ? 0xffffffffu : ~((1u << a.low_bit) - 1u));
+    if (a.dbg != nullptr && tid == 0) a.dbg[4] = gtime();
     // kth = k-th largest key (low insignificant bits zero). Strictly greater keys first (ascending index), then
     // keys equal to it (ascending index) until k are written: torch's CUDA radix-select order.
     const uint32_t mask = a.low_bit == 0 ? 0xffffffffu : ~((1u << a.low_bit) - 1u);
@@ -216,18 +254,22 @@ __device__ void select_row(const GateArgs& a, int r, int* s_hist) {
         }
         n_greater += s_hist[64 + w];
     }
-    const int remaining = a.k - n_greater;
+    remaining = a.k - n_greater;  // ties taken (equals the search's residual count)
     int pg = bg + ig - cg, pe = be + ie - ce;
-    for (int j = 0; j < (in_regs ? KPT : per); ++j) {
-        const int i = lo + j;
-        if (i >= hi) break;
-        const uint32_t key = (in_regs ? keys[j] : order_key(__ldcg(norm + i))) & mask;
+    auto emit = [&](int i, uint32_t key) {
         if (key > kth) {
             out[pg++] = i;
         } else if (key == kth) {
             if (pe < remaining) out[n_greater + pe] = i;
             ++pe;
         }
+    };
+    if (in_regs) {  // static indices only: the key array must stay in registers
+#pragma unroll
+        for (int j = 0; j < KPT; ++j)
+            if (lo + j < hi) emit(lo + j, keys[j] & mask);
+    } else {
+        for (int i = lo; i < hi; ++i) emit(i, order_key(__ldcg(norm + i)) & mask);
     }
 }
 
@@ -236,8 +278,10 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
     constexpr int VEC = ElemTraits<T>::VEC;
     constexpr int GROUPS = kGateThreads / LPT;
     __shared__ int s_hist[128];
+    __shared__ uint32_t s_keys[kSmemKeys];
     __shared__ int s_misc[4];
 
+    if (a.dbg != nullptr && threadIdx.x == 0) atomicMin(a.dbg + 0, gtime());
     const int r = blockIdx.y;
     const int lane = threadIdx.x % LPT;
     const int group = threadIdx.x / LPT;
@@ -249,6 +293,21 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
     T* xsum = static_cast<T*>(a.xsum);
     const T* p = static_cast<const T*>(a.p);
     const int iters = (a.tokens_per_cta + GROUPS - 1) / GROUPS;
+    // LayerNorm affine parameters: one copy per CTA in shared memory (overlaid on the key buffer, which is only
+    // used by the selection stage afterwards) instead of every warp re-reading the same L2 lines per token
+    const T* ln_w = static_cast<const T*>(a.ln_w);
+    const T* ln_b = static_cast<const T*>(a.ln_b);
+    if (ln_w != nullptr && (size_t)a.D * sizeof(T) * 2 <= sizeof(s_keys)) {
+        T* sw = reinterpret_cast<T*>(s_keys);
+        T* sb = sw + a.D;
+        for (int c = threadIdx.x; c < nchunks; c += kGateThreads) {
+            st16(sw + (size_t)c * VEC, ld16(ln_w + (size_t)c * VEC));
+            st16(sb + (size_t)c * VEC, ld16(ln_b + (size_t)c * VEC));
+        }
+        __syncthreads();
+        ln_w = sw;
+        ln_b = sb;
+    }
 
     for (int it = 0; it < iters; ++it) {
         const int tok = t0 + it * GROUPS + group;
@@ -264,9 +323,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
             }
         }
         load_row<T, LPT, CPL>(xa, xb, xsum, off, nchunks, lane, valid, v);
-        if (a.ln_w != nullptr)
-            layer_norm_row<T, LPT, CPL>(v, static_cast<const T*>(a.ln_w), static_cast<const T*>(a.ln_b), nchunks,
-                                        lane, a.D, a.eps);
+        if (ln_w != nullptr) layer_norm_row<T, LPT, CPL>(v, ln_w, ln_b, nchunks, lane, a.D, a.eps);
         float ss = 0.f;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
@@ -284,6 +341,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
         if (valid && lane == 0) a.norm[(size_t)r * a.N + tok] = round_to<T>(sqrtf(ss));
     }
 
+    if (a.dbg != nullptr && threadIdx.x == 0) atomicMax(a.dbg + 1, gtime());
     // ---- last CTA of this row runs the selection (threadFenceReduction pattern)
     __threadfence();
     __syncthreads();
@@ -294,7 +352,10 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
     __syncthreads();
     if (!s_misc[2]) return;
     __threadfence();
-    select_row(a, r, s_hist);
+    if (a.dbg != nullptr && threadIdx.x == 0) a.dbg[2] = gtime();
+    if (a.N <= 16 * kGateThreads) select_row<16>(a, r, s_hist, s_keys);
+    else select_row<32>(a, r, s_hist, s_keys);
+    if (a.dbg != nullptr && threadIdx.x == 0) a.dbg[5] = gtime();
     if (threadIdx.x == 0) a.ticket[r] = 0;  // self-reset so the workspace is reusable / graph-replayable
 }
 
@@ -549,7 +610,7 @@ int et_gate_select(const void* xa, const void* xb, void* xsum_out, const void* l
                    const void* p, int64_t R, int64_t N, int64_t D, int dtype, int mode, int64_t k, float threshold,
                    float* norm_out, int64_t* idx_out, int32_t* count_out, int32_t* ticket, void* stream) {
     ET_CHECK_ARG(xa && norm_out && idx_out && ticket, "et_gate_select: null pointer");
-    ET_CHECK_ARG(R > 0 && N > 0 && D > 0 && R <= 65535 && N < (1 << 30), "et_gate_select: bad shape R=%lld N=%lld D=%lld",
+    ET_CHECK_ARG(R > 0 && N > 0 && D > 0 && R <= 65535 && N <= 524280, "et_gate_select: bad shape R=%lld N=%lld D=%lld",
                  (long long)R, (long long)N, (long long)D);
     ET_CHECK_ARG((ln_w == nullptr) == (ln_b == nullptr), "et_gate_select: ln_w / ln_b must both be set or both null");
     ET_CHECK_ARG(et_aligned16(xa) && et_aligned16(xb) && et_aligned16(xsum_out) && et_aligned16(p) &&
@@ -566,6 +627,7 @@ int et_gate_select(const void* xa, const void* xb, void* xsum_out, const void* l
     a.xa = xa; a.xb = xb; a.xsum = xsum_out; a.ln_w = ln_w; a.ln_b = ln_b; a.eps = ln_eps; a.p = p;
     a.N = (int)N; a.D = (int)D; a.mode = mode; a.k = (int)k; a.norm = norm_out;
     a.idx = reinterpret_cast<long long*>(idx_out); a.count = count_out; a.ticket = ticket;
+    a.dbg = g_gate_dbg;
     int rc = ET_OK;
     ET_DISPATCH_DTYPE(dtype, T, {
         constexpr int VEC = ElemTraits<T>::VEC;
@@ -573,7 +635,7 @@ int et_gate_select(const void* xa, const void* xb, void* xsum_out, const void* l
         const int nchunks = (int)D / VEC;
         const int lpt = nchunks <= 1 ? 1 : nchunks <= 2 ? 2 : nchunks <= 4 ? 4 : nchunks <= 8 ? 8 : nchunks <= 16 ? 16 : 32;
         const int groups = kGateThreads / lpt;
-        // ~2 CTAs per SM over the whole launch, each CTA at least one pass of its token groups
+        // ~4 CTAs per SM over the whole launch (all resident: more loads in flight), each CTA at least one pass
         long long want = (2 * 148 + R - 1) / R;
         long long max_ctas = (N + groups - 1) / groups;
         long long ctas = want < 1 ? 1 : (want > max_ctas ? max_ctas : want);

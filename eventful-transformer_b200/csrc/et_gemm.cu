@@ -206,6 +206,7 @@ int g_force_block_n = 0;  // test hook: et_debug_set(1, BLOCK_N)
 }  // namespace
 
 extern int g_attn_tc;
+extern unsigned long long* g_gate_dbg;
 
 extern "C" {
 
@@ -216,6 +217,10 @@ int et_debug_set(int key, long long value) {
     }
     if (key == 2) {
         g_attn_tc = value != 0;
+        return ET_OK;
+    }
+    if (key == 3) {
+        g_gate_dbg = reinterpret_cast<unsigned long long*>(value);
         return ET_OK;
     }
     return et_fail(ET_ERR_ARG, "et_debug_set: unknown key %d", key);

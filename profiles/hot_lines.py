@@ -20,10 +20,11 @@ for r in csv.reader(out.splitlines()):
         hdr = r
     elif hdr is not None and r[0].isdigit() and len(r) >= len(hdr) - 2:
         col = {c: i for i, c in enumerate(hdr)}
-        n = int(r[col["# Samples"]] or 0)
+        raw = r[col["# Samples"]]
+        n = int(raw) if raw.isdigit() else 0
         stalls = {}
         for i, c in enumerate(hdr):
-            if c.startswith("stall_") and "Not Issued" not in c and i < len(r) and r[i] not in ("", "0", "-"):
+            if c.startswith("stall_") and "Not Issued" not in c and i < len(r) and r[i].isdigit() and r[i] != "0":
                 stalls[c[6:]] = int(r[i])
         lines.append((n, path, int(r[0]), r[1].strip()[:90], sorted(stalls.items(), key=lambda kv: -kv[1])[:2],
                       r[col["Instructions Executed"]]))
