@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_apply_kernel(const AttnArgs
 // DELTA: for each selected row: dV = v - p_v, Vd = v - dV, p_v = v.   FIRST: p_v = v for every token.
 template <typename T>
 __global__ void __launch_bounds__(256) vgate_kernel(const T* qkv, T* v_state, const long long* idx, T* Ksel, T* dV, T* Vd,
-                                                    int N, int D, int k, long long total_vec) {
+                                                    int N, int D, int k, long long total_vec, int emit_vn) {
     const int nch = D / 8;
     for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total_vec;
          gi += (long long)gridDim.x * blockDim.x) {
@@ -670,7 +670,8 @@ __global__ void __launch_bounds__(256) vgate_kernel(const T* qkv, T* v_state, co
                 d[i] = round_to<T>(vn[i] - pv[i]);
                 r[i] = vn[i] - d[i];
             }
-            st16(dV + (size_t)row * D + (size_t)ch * 8, pack16<T>(d));
+            // tensor-core path consumes v_n (acc += a_n . v_n - p . (v_n - dV)); the mma.sync path consumes dV
+            st16(dV + (size_t)row * D + (size_t)ch * 8, emit_vn ? vraw : pack16<T>(d));
             st16(Vd + (size_t)row * D + (size_t)ch * 8, pack16<T>(r));
         }
         st16(v_state + st, vraw);
@@ -754,14 +755,15 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
         const long long total = (long long)a.B * a.k * (D / 8);
         if (total > 0)
             vgate_kernel<T><<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, static_cast<T*>(v_state), a.idx,
-                                                                      use_tc ? Ksel : nullptr, dV, Vd, a.N, D, a.k, total);
+                                                                      use_tc ? Ksel : nullptr, dV, Vd, a.N, D, a.k, total,
+                                                                      use_tc ? 1 : 0);
         ET_COUNT_LAUNCH(1);
         args.dV = dV;
         args.Vd = Vd;
     } else if (a.mode == ET_ATTN_FIRST) {
         const long long total = (long long)a.B * a.N * (D / 8);
         vgate_kernel<T><<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, static_cast<T*>(v_state), nullptr, nullptr, nullptr,
-                                                                  nullptr, a.N, D, a.N, total);
+                                                                  nullptr, a.N, D, a.N, total, 0);
         ET_COUNT_LAUNCH(1);
     }
     if (use_tc) {

@@ -11,11 +11,17 @@
 //                                    rel-pos bias (eventful_transformer/utils.py:157-166) comes out of the MMA and the
 //                                    softmax threads do no table lookups;
 //                               a_n = exp2(S' c1 - m2) / l, rounded to dtype exactly as stored in the gate state;
-//                               A-gate: dA = a_n - a_state[:, idx]; a_state[:, idx] = a_n  (column-major state: a
-//                                    selected column is 256 contiguous bytes per query block; 16-byte cp.async in,
-//                                    128-bit stores out, by the producer warp);
-//                               O += a_n . dV + dA . (v_n - dV): two tcgen05 MMAs, P tiles from smem (K-major,
-//                                    128B swizzle), V tiles as MN-major B operands straight from TMA;
+//                               A-gate + accumulator in one algebraic step.  The reference computes
+//                                    acc += a_n . dV + (a_n - p) . (v_n - dV)            (modules.py:293-294)
+//                                    and since dV + (v_n - dV) = v_n this equals
+//                                    acc += a_n . v_n  -  p . (v_n - dV)
+//                                    so the OLD state tile p = a_state[:, idx] is fed to the tensor core directly
+//                                    (negated A operand, fp32 accumulate) and no thread ever reads it.  The state is
+//                                    column-major: a selected column is 256 contiguous bytes per query block, moved
+//                                    by 16-byte cp.async into an MN-major, 128B-swizzled A tile; a_n is written once
+//                                    by the softmax threads into a tile of the same layout, which is both the A
+//                                    operand of a_n . v_n and the source of the write-back a_state[:, idx] = a_n.
+//                                    V tiles are MN-major B operands straight from TMA.
 //                               epilogue: acc += O; out = acc.
 //                    FIRST / DENSE modes run the same pipeline over all keys with V from the QKV buffer.
 // Warp roles (320 threads): warp 0 = TMA / cp.async producer + state write-back, warp 1 = TMEM allocator and
@@ -225,12 +231,12 @@ constexpr int AP_KEYS = 64;
 constexpr int AP_BLK = AP_KEYS * 64 * 2;          // 8 KB: one 64-key x 64-column operand block
 constexpr int AP_STAGE = 5 * AP_BLK;              // K, onehot-y, onehot-x, V1, V2
 constexpr int AP_PT = AP_KEYS * QROWS * 2;        // 16 KB: a_state tile [key][row]
-constexpr int AP_P = QROWS * AP_KEYS * 2;         // 16 KB: P tile (A operand)
+constexpr int AP_P = QROWS * AP_KEYS * 2;         // 16 KB: a_n tile (A operand, MN-major) = write-back staging
 constexpr int AP_OFF_ST = 3 * QROWS * 128;        // Q' = three 16 KB blocks: q, 8 bias_h, 8 bias_w
 constexpr int AP_OFF_PT = AP_OFF_ST + 2 * AP_STAGE;
 constexpr int AP_PT_STAGES = 3;                   // a_state tiles are prefetched three tiles ahead by the softmax threads
 constexpr int AP_OFF_P = AP_OFF_PT + AP_PT_STAGES * AP_PT;
-constexpr int AP_OFF_MISC = AP_OFF_P + 2 * AP_P;
+constexpr int AP_OFF_MISC = AP_OFF_P + AP_P;
 constexpr int AP_SMEM = AP_OFF_MISC + 1024 + 1024;
 
 template <bool BF16, int MODE>
@@ -244,9 +250,11 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     auto Kb = [&](int u, int i) { return smem + AP_OFF_ST + u * AP_STAGE + i * AP_BLK; };  // 0 k, 1 oh-y, 2 oh-x
     auto V1 = [&](int u) { return smem + AP_OFF_ST + u * AP_STAGE + 3 * AP_BLK; };
     auto V2 = [&](int u) { return smem + AP_OFF_ST + u * AP_STAGE + 4 * AP_BLK; };
-    auto Pt = [&](int u) { return reinterpret_cast<uint16_t*>(smem + AP_OFF_PT + u * AP_PT); };
-    uint8_t* Pn = smem + AP_OFF_P;
-    uint8_t* Pd = smem + AP_OFF_P + AP_P;
+    // MN-major A tiles [64 keys][128 rows]: two 8 KB blocks of 64 rows; key kk = one 128-byte line per block,
+    // its 16-byte chunk c (8 rows) stored at chunk position c ^ (kk & 7)
+    auto Pt = [&](int u) { return smem + AP_OFF_PT + u * AP_PT; };
+    uint8_t* An = smem + AP_OFF_P;
+    auto a_chunk = [](int key, int seg) { return (seg >> 3) * 8192 + key * 128 + (((seg & 7) ^ (key & 7)) << 4); };
     int* s_tok = reinterpret_cast<int*>(smem + AP_OFF_MISC);  // [2][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AP_OFF_MISC + 512);
     uint64_t* q_full = bars;
@@ -336,7 +344,9 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc_ex(128, AP_KEYS, a.is_bf16, 0);
-            const uint32_t idesc_o = umma_idesc_ex(128, 64, a.is_bf16, 1);  // B = V tile, MN-major
+            // PV products: A = [key][row] tiles (MN-major), B = V tiles (MN-major); the p . Vd product is subtracted
+            const uint32_t idesc_o = umma_idesc_ex(128, 64, a.is_bf16, 1) | (1u << 15);
+            const uint32_t idesc_neg = idesc_o | (1u << 13);  // a_negate
             mbar_wait(smem_u32(q_full), 0);
             auto issue_s = [&](int t) {
                 const int u = t & 1;
@@ -357,17 +367,19 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const int u = t & 1;
                 mbar_wait(smem_u32(p_ready), t & 1);
                 tcgen05_fence_after();
-                const uint64_t dpn = umma_smem_desc(smem_u32(Pn));
+                const uint64_t dan = umma_smem_desc_mn_a(smem_u32(An));
                 const uint64_t dv1 = umma_smem_desc_mn(smem_u32(V1(u)));
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)  // 16 keys per step: +32 B in P rows, +16 rows (2048 B) in the V tile
-                    tcgen05_mma_f16(tmem_o, dpn + (uint64_t)(2 * kk), dv1 + (uint64_t)(128 * kk), idesc_o, (t > 0 || kk > 0));
+                for (int kk = 0; kk < 4; ++kk)  // 16 keys per step = 16 lines of 128 B (2048 B) in the A and V tiles
+                    tcgen05_mma_f16(tmem_o, dan + (uint64_t)(128 * kk), dv1 + (uint64_t)(128 * kk), idesc_o, (t > 0 || kk > 0));
                 if (MODE == ET_ATTN_DELTA) {
-                    const uint64_t dpd = umma_smem_desc(smem_u32(Pd));
+                    mbar_wait(smem_u32(&ps_full[t % AP_PT_STAGES]), (t / AP_PT_STAGES) & 1);  // old state tile landed
+                    fence_proxy_async();  // cp.async (generic proxy) writes -> visible to the tensor core
+                    const uint64_t dp = umma_smem_desc_mn_a(smem_u32(Pt(t % AP_PT_STAGES)));
                     const uint64_t dv2 = umma_smem_desc_mn(smem_u32(V2(u)));
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
-                        tcgen05_mma_f16(tmem_o, dpd + (uint64_t)(2 * kk), dv2 + (uint64_t)(128 * kk), idesc_o, 1u);
+                        tcgen05_mma_f16(tmem_o, dp + (uint64_t)(128 * kk), dv2 + (uint64_t)(128 * kk), idesc_neg, 1u);
                 }
                 tcgen05_commit(smem_u32(&pv_done[u]));
                 if (t == T - 1) tcgen05_commit(smem_u32(o_full));
@@ -387,8 +399,9 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const float m2 = a.stats[grow * 2];
         const float linv = 1.f / a.stats[grow * 2 + 1];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        uint8_t* pn_row = Pn + (row >> 3) * 1024 + (row & 7) * 128;
-        uint8_t* pd_row = Pd + (row >> 3) * 1024 + (row & 7) * 128;
+        // this thread's element (key, row) of an MN-major A tile: block row >> 6, line key, chunk (row >> 3) & 7
+        const int a_row_off = (row >> 6) * 8192 + (row & 7) * 2;
+        const int a_row_chunk = (row >> 3) & 7;
         // A-gate state traffic is spread over the 256 softmax threads: a selected column x this CTA's 128 rows is 256
         // contiguous bytes = 16 threads x 16 B; thread st moves segment (st & 15) of columns (st >> 4) + 16 i, i < 4.
         const int st = threadIdx.x - 64;
@@ -398,13 +411,14 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (j >= nkeys) return -1;
             return (MODE == ET_ATTN_DELTA) ? (int)a.idx[(size_t)b * a.k + j] : j;
         };
-        auto load_state = [&](int tt, const int (&tok)[4]) {  // a_state[:, idx of tile tt] -> Pt ring
-            uint16_t* dst = Pt(tt % AP_PT_STAGES);
+        auto load_state = [&](int tt, const int (&tok)[4]) {  // a_state[:, idx of tile tt] -> Pt ring (A-operand layout)
+            uint8_t* dst = Pt(tt % AP_PT_STAGES);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (tok[i] >= 0)
-                    cp_async_16(smem_u32(dst + (col0 + 16 * i) * QROWS + seg),
-                                a_state + a_head + (size_t)tok[i] * a.NP + q0 + seg);
+            for (int i = 0; i < 4; ++i) {
+                uint8_t* d = dst + a_chunk(col0 + 16 * i, st & 15);
+                if (tok[i] >= 0) cp_async_16(smem_u32(d), a_state + a_head + (size_t)tok[i] * a.NP + q0 + seg);
+                else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);  // ragged tile: p = 0, never garbage
+            }
             cp_async_arrive_noinc(smem_u32(&ps_full[tt % AP_PT_STAGES]));
         };
         int tok_next[4] = {-1, -1, -1, -1};  // tokens of the tile AP_PT_STAGES ahead (index loads issued a tile early)
@@ -431,67 +445,52 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_empty[u]));
             const int* tk = s_tok + u * AP_KEYS + half * 32;
+            const bool full_tile = (t + 1) * AP_KEYS <= nkeys;
             // normalised attention values of the selected columns, rounded to dtype exactly as stored in the state
-            uint32_t an[16], ad[16];  // element pairs: key 2i in the low half of word i
+            uint32_t an[16];  // element pairs: key 2i in the low half of word i
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), a.c1, -m2)) * linv;
                 const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), a.c1, -m2)) * linv;
-                const uint32_t e0 = tk[2 * i] >= 0 ? float_to_elem<BF16>(p0) : 0u;
-                const uint32_t e1 = tk[2 * i + 1] >= 0 ? float_to_elem<BF16>(p1) : 0u;
-                an[i] = e0 | (e1 << 16);
+                an[i] = float_to_elem<BF16>(p0) | (float_to_elem<BF16>(p1) << 16);
             }
-            const int ps = t % AP_PT_STAGES;
-            if (MODE == ET_ATTN_DELTA) {
-                mbar_wait(smem_u32(&ps_full[ps]), (t / AP_PT_STAGES) & 1);
-                uint16_t* pt = Pt(ps) + (half * 32) * QROWS + row;
+            if (!full_tile) {  // ragged last tile: keys beyond k contribute nothing
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const uint16_t c0 = (uint16_t)(an[i] & 0xffffu), c1 = (uint16_t)(an[i] >> 16);
-                    const float prev0 = tk[2 * i] >= 0 ? elem_to_float<BF16>(pt[(2 * i) * QROWS]) : 0.f;
-                    const float prev1 = tk[2 * i + 1] >= 0 ? elem_to_float<BF16>(pt[(2 * i + 1) * QROWS]) : 0.f;
-                    // dA = a_n - p (modules.py:196), p[:, idx] = a_n (modules.py:200)
-                    ad[i] = float_to_elem<BF16>(elem_to_float<BF16>(c0) - prev0) |
-                            (float_to_elem<BF16>(elem_to_float<BF16>(c1) - prev1) << 16);
-                    pt[(2 * i) * QROWS] = c0;
-                    pt[(2 * i + 1) * QROWS] = c1;
-                }
-            } else if (MODE == ET_ATTN_FIRST) {
-                uint16_t* pt = Pt(ps) + (half * 32) * QROWS + row;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    pt[(2 * i) * QROWS] = (uint16_t)(an[i] & 0xffffu);
-                    pt[(2 * i + 1) * QROWS] = (uint16_t)(an[i] >> 16);
+                    if (tk[2 * i] < 0) an[i] &= 0xffff0000u;
+                    if (tk[2 * i + 1] < 0) an[i] &= 0x0000ffffu;
                 }
             }
-            if (t >= 1) mbar_wait(smem_u32(&pv_done[(t - 1) & 1]), ((t - 1) >> 1) & 1);  // single P buffer: tile t-1 consumed
-            // P tiles as K-major, 128-byte-swizzled A operands: row r, 16-byte chunk c -> c ^ (r % 8)
+            if (t >= 1) mbar_wait(smem_u32(&pv_done[(t - 1) & 1]), ((t - 1) >> 1) & 1);  // a_n tile of t-1 consumed
+            {
+                uint8_t* dst = An + a_row_off;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int sw = ((half * 4 + c) ^ (row & 7)) * 16;
-                *reinterpret_cast<uint4*>(pn_row + sw) = make_uint4(an[c * 4], an[c * 4 + 1], an[c * 4 + 2], an[c * 4 + 3]);
-                if (MODE == ET_ATTN_DELTA)
-                    *reinterpret_cast<uint4*>(pd_row + sw) = make_uint4(ad[c * 4], ad[c * 4 + 1], ad[c * 4 + 2], ad[c * 4 + 3]);
+                for (int i = 0; i < 16; ++i) {
+                    const int k0 = half * 32 + 2 * i, k1 = k0 + 1;
+                    *reinterpret_cast<uint16_t*>(dst + k0 * 128 + ((a_row_chunk ^ (k0 & 7)) << 4)) = (uint16_t)(an[i] & 0xffffu);
+                    *reinterpret_cast<uint16_t*>(dst + k1 * 128 + ((a_row_chunk ^ (k1 & 7)) << 4)) = (uint16_t)(an[i] >> 16);
+                }
             }
             fence_proxy_async();  // generic-proxy smem writes -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(p_ready));
             if (MODE != ET_ATTN_DENSE) {
-                // write the updated columns back (a_state[:, idx] = a_n) and refill the ring slot three tiles ahead
-                asm volatile("bar.sync 1, 256;" ::: "memory");  // every row of the tile is in Pt(ps)
+                // write the updated columns back: a_state[:, idx] = a_n (modules.py:200)
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // every row of the a_n tile is written
                 uint4 wb[4];
                 int tk_wb[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     tk_wb[i] = s_tok[u * AP_KEYS + col0 + 16 * i];
-                    wb[i] = *reinterpret_cast<const uint4*>(Pt(ps) + (col0 + 16 * i) * QROWS + seg);
+                    wb[i] = *reinterpret_cast<const uint4*>(An + a_chunk(col0 + 16 * i, st & 15));
                 }
-                asm volatile("bar.sync 2, 256;" ::: "memory");  // all reads of the slot done: it may be refilled
-                if (MODE == ET_ATTN_DELTA && t + AP_PT_STAGES < T) {
-                    load_state(t + AP_PT_STAGES, tok_next);
-                    if (t + AP_PT_STAGES + 1 < T) {
+                asm volatile("bar.sync 2, 256;" ::: "memory");  // all chunks read: the a_n tile may be rewritten
+                // refill the p ring: the slot of tile t - 1 is free once its PV MMAs are done (pv_done(t-1), waited above)
+                if (MODE == ET_ATTN_DELTA && t >= 1 && t - 1 + AP_PT_STAGES < T) {
+                    load_state(t - 1 + AP_PT_STAGES, tok_next);
+                    if (t + AP_PT_STAGES < T) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) tok_next[i] = tile_tok(t + AP_PT_STAGES + 1, i);
+                        for (int i = 0; i < 4; ++i) tok_next[i] = tile_tok(t + AP_PT_STAGES, i);
                     }
                 }
 #pragma unroll
@@ -608,7 +607,7 @@ int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, i
 }  // namespace
 
 // Entry used by et_global_attention (et_attn.cu) when the shape qualifies for the tensor-core path.
-// `sel` = workspace rows [K_sel | dV | v_n - dV], each (B * k, D); `onehot` = (max(B * k, N), 128) scratch;
+// `sel` = workspace rows [K_sel | v_n | v_n - dV], each (B * k, D); `onehot` = (max(B * k, N), 128) scratch;
 // bias tables in the tc layout: (B, H, N, 64) each, holding 8 x bias, zero padded.
 int et_tc_global_attention(const void* qkv, const void* sel, void* onehot, const void* bias_h, const void* bias_w, int mode,
                            const long long* idx, int k, void* a_state, void* acc, void* out, float* stats, int B, int N,

@@ -128,6 +128,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // MN-major operand tile (rows = K index, 128-byte rows of 64 contiguous MN elements), 128-byte swizzle:
 // 8-row groups 1024 bytes apart (SBO); a single 64-element MN block, so LBO is unused.
 __device__ __forceinline__ uint64_t umma_smem_desc_mn(uint32_t smem_addr) { return umma_smem_desc(smem_addr); }
+// MN-major A tile of 128 rows = two 64-row blocks 8192 bytes apart (leading byte offset), 8-line groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_smem_desc_mn_a(uint32_t smem_addr) {
+    uint64_t d = umma_smem_desc(smem_addr);
+    d &= ~((uint64_t)0x3fff << 16);
+    d |= (uint64_t)(8192 >> 4) << 16;
+    return d;
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
