@@ -27,6 +27,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "eventful-transformer_b200"))
 
+import et_streams  # noqa: E402
 import et_synthetic as syn  # noqa: E402
 
 METRIC = "ViTDet-B Eventful backbone frames/s (1024x1024, k=2048 of 4096 tokens, incremental frames)"
@@ -117,8 +118,11 @@ def make_backbone(grid, block_class, windowed_class, k, device, dtype):
     return model
 
 
-def make_frames(streams, n_tokens, dim, seed):
-    return syn.token_stream(streams, n_tokens, dim, RING, seed=seed, mode="drift", dtype=torch.bfloat16)
+def make_frames(stream_ids, n_tokens, dim):
+    """RING frames of shape (len(stream_ids), N, D); each stream's video depends only on its global id."""
+    per_stream = [syn.token_stream(1, n_tokens, dim, RING, seed=et_streams.stream_seed(100, sid), mode="drift",
+                                   dtype=torch.bfloat16) for sid in stream_ids]
+    return [torch.cat([frames[t] for frames in per_stream], dim=0) for t in range(RING)]
 
 
 def timed_steps(step, steps, dist_ctx):
@@ -384,7 +388,9 @@ def main():
     dev, dt = torch.device("cuda", local), torch.bfloat16
     pk = peaks()
     model = make_backbone(grid, "EventfulBlock", "EventfulTokenwiseBlock", args.k, dev, dt)
-    frames_host = [f.pin_memory() for f in make_frames(args.streams, n, d, seed=100 + rank)]
+    total_streams = args.streams * world  # weak scaling: a fixed stream group per GPU
+    my_streams = et_streams.partition_streams(total_streams, world, rank)
+    frames_host = [f.pin_memory() for f in make_frames(my_streams, n, d)]
     frames_dev = [f.to(dev) for f in frames_host]
     use_graph = not args.no_graph
 
@@ -410,9 +416,8 @@ def main():
 
     # ---- NCCL only collects outputs (outside the timed region)
     if dist_ctx is not None:
-        gathered = [torch.empty_like(stage) for _ in range(world)]
-        dist_ctx.all_gather(gathered, out_host.to(dev))
-        assert all(torch.isfinite(t.float()).all() for t in gathered)
+        gathered = et_streams.gather_stream_outputs(out_host.to(dev), my_streams, total_streams, dist_ctx)
+        assert gathered.shape[0] == total_streams and bool(torch.isfinite(gathered.float()).all())
 
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(3, args.warmup), ms_per_step=round(ms / args.steps, 4), higher_is_better=True, scaling="weak",
