@@ -18,6 +18,8 @@
 int et_tc_global_attention(const void* qkv, const void* sel, void* onehot, const void* bias_h, const void* bias_w, int mode,
                            const long long* idx, int k, void* a_state, void* acc, void* out, float* stats, int B, int N,
                            int NP, int H, int gh, int gw, int is_bf16, cudaStream_t stream);
+int et_tc_window_attention(const void* qkv, const void* pad_token, void* bias_comb, void* out, int B, int N, int gh, int gw,
+                           int wh, int ww, int H, int has_bias, int is_bf16, cudaStream_t s);
 int g_attn_tc = 1;  // et_debug_set(2, 0) forces the mma.sync kernels (tests compare the two paths)
 
 namespace {
@@ -184,7 +186,8 @@ __device__ __forceinline__ void add_bias(float (&s)[8][4], const T* bh, const T*
 // bias[token][coord] = q[token] . table[coord]  -> a small tensor-core GEMM per line (mma.sync m16n8k16).
 template <typename T, int DH>
 __global__ void __launch_bounds__(kAttnThreads) relpos_bias_kernel(const AttnArgs a, const T* rel_y, const T* rel_x,
-                                                                    T* bias_h, T* bias_w, int ld_pad, float scale) {
+                                                                    T* bias_h, T* bias_w, int ld_pad, float scale,
+                                                                    int rows_pad, int combined) {
     constexpr int LD = DH + 8;
     __shared__ __align__(16) T Qs[BQ * LD];
     __shared__ __align__(16) T Ts[BKV * LD];
@@ -228,10 +231,14 @@ __global__ void __launch_bounds__(kAttnThreads) relpos_bias_kernel(const AttnArg
                 for (int i = 0; i < 4; ++i) {
                     const int j = tok0 + warp * 16 + g + (i >> 1) * 8;
                     const int kc = out0 + nt * 8 + tq * 2 + (i & 1);
-                    const int ld = ld_pad > 0 ? ld_pad : nout;  // ld_pad: tc layout, rows zero padded to ld_pad columns
-                    if (j < ntok && kc < ld) {
+                    // ld_pad: tensor-core layouts with padded rows. combined: one array [bias_h | bias_w | 0] per token
+                    // (pre-zeroed by the caller, bias_w == bias_h); otherwise the pad columns are zero-filled here.
+                    const int ld = ld_pad > 0 ? ld_pad : nout;
+                    const int rows = rows_pad > 0 ? rows_pad : a.Wn;
+                    const int coff = (combined && !ymode) ? lh : 0;
+                    if (j < ntok && kc < (combined ? nout : ld)) {
                         const int t = ymode ? fixed * lw + j : j * lw + fixed;
-                        dst[(((size_t)bw * a.H + h) * a.Wn + t) * ld + kc] =
+                        dst[(((size_t)bw * a.H + h) * rows + t) * ld + coff + kc] =
                             ElemTraits<T>::from_float(kc < nout ? s[nt][i] * scale : 0.f);
                     }
                 }
@@ -712,11 +719,24 @@ int run_window(const AttnArgs& a, const void* rel_y, const void* rel_x, void* bi
     const int lh = a.windowed ? a.wh : a.gh, lw = a.windowed ? a.ww : a.gw;
     const int nwin = a.windowed ? a.nwx * a.nwy : 1;
     AttnArgs args = a;
+    // tensor-core path: real windows of at most 208 tokens, dh = 64, rel-pos coordinates fitting one 64-column block
+    if (a.windowed && DH == 64 && a.Wn <= 208 && (rel_y == nullptr || lh + lw <= 64) && g_attn_tc) {
+        if (rel_y != nullptr) {
+            T* comb = static_cast<T*>(bias_ws);
+            const size_t bytes = (size_t)a.B * nwin * a.H * 256 * 64 * sizeof(T);
+            if (cudaMemsetAsync(comb, 0, bytes, s) != cudaSuccess) return et_fail(ET_ERR_CUDA, "cudaMemsetAsync failed");
+            relpos_bias_kernel<T, DH><<<dim3(lh + lw, a.H, a.B * nwin), kAttnThreads, 0, s>>>(
+                a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), comb, comb, 64, 8.f, 256, 1);
+            ET_COUNT_LAUNCH(1);
+        }
+        return et_tc_window_attention(a.qkv, a.pad_token, bias_ws, a.out, a.B, a.N, a.gh, a.gw, a.wh, a.ww, a.H,
+                                      rel_y != nullptr ? 1 : 0, std::is_same_v<T, __nv_bfloat16> ? 1 : 0, s);
+    }
     if (rel_y != nullptr) {
         T* bh = static_cast<T*>(bias_ws);
         T* bw = bh + align8((size_t)a.B * nwin * a.H * a.Wn * lh);
         relpos_bias_kernel<T, DH><<<dim3(lh + lw, a.H, a.B * nwin), kAttnThreads, 0, s>>>(
-            a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw, 0, 1.f);
+            a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw, 0, 1.f, 0, 0);
         ET_COUNT_LAUNCH(1);
         args.bias_h = bh;
         args.bias_w = bw;
@@ -745,7 +765,7 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     T* onehot = Vd + (size_t)a.B * a.k * D;
     if (rel_y != nullptr) {
         relpos_bias_kernel<T, DH><<<dim3(a.gh + a.gw, a.H, a.B), kAttnThreads, 0, s>>>(
-            a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw, use_tc ? 64 : 0, use_tc ? 8.f : 1.f);
+            a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw, use_tc ? 64 : 0, use_tc ? 8.f : 1.f, 0, 0);
         ET_COUNT_LAUNCH(1);
         args.bias_h = bh;
         args.bias_w = bw;
@@ -813,6 +833,7 @@ int64_t et_attn_workspace_bytes(int64_t B, int64_t N, int64_t gh, int64_t gw, in
     if (wh > 0) {
         const int64_t nw = ((gh + wh - 1) / wh) * ((gw + ww - 1) / ww);
         if (has_relpos) elems += align8(B * nw * heads * wh * ww * wh) + align8(B * nw * heads * wh * ww * ww);
+        if (has_relpos) elems += B * nw * heads * 256 * 64 + 256 * 64;  // tensor-core layout: combined bias rows + one-hot block
     } else {
         // upper bound over both layouts (the tensor-core path pads bias rows to 64 columns and adds a one-hot scratch)
         if (has_relpos) elems += align8(B * heads * N * (gh > 64 ? gh : 64)) + align8(B * heads * N * (gw > 64 ? gw : 64));

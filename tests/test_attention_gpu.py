@@ -160,3 +160,19 @@ def test_tensor_core_dense_global_attention():
     want = oracle._attention_dense(0, qkv.float())
     blk = gpu_block("EventfulMatmul1Block", dim, heads, grid, params, rel=rel)
     assert rel_err(blk._attention_incremental(qkv.to(DEV), None).cpu(), want) < 2e-2
+
+
+@pytest.mark.parametrize("grid,batch", [((16, 16), 2), ((64, 64), 1), ((28, 42), 1)])
+def test_tensor_core_window_path_agrees_with_mma_sync_path(grid, batch):
+    dim, heads, window = 768, 12, (14, 14)
+    params = block_params(dim, heads, window, seed=23, std=0.3)
+    qkv = torch.randn(batch, grid[0] * grid[1], 3 * dim, generator=torch.Generator().manual_seed(10)).to(DT).to(DEV)
+    outs = []
+    try:
+        for flag in (1, 0):
+            native.lib().et_debug_set(2, flag)
+            blk = gpu_block("EventfulTokenwiseBlock", dim, heads, grid, params, rel=(64, 64), window=window)
+            outs.append(blk._dense_attention(qkv).clone())
+    finally:
+        native.lib().et_debug_set(2, 1)
+    assert rel_err(outs[0], outs[1]) < 1.5e-2
