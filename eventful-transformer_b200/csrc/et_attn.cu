@@ -188,6 +188,7 @@ template <typename T, int DH>
 __global__ void __launch_bounds__(kAttnThreads) relpos_bias_kernel(const AttnArgs a, const T* rel_y, const T* rel_x,
                                                                     T* bias_h, T* bias_w, int ld_pad, float scale,
                                                                     int rows_pad, int combined) {
+    et_pdl_prologue();
     constexpr int LD = DH + 8;
     __shared__ __align__(16) T Qs[BQ * LD];
     __shared__ __align__(16) T Ts[BKV * LD];
@@ -246,10 +247,79 @@ __global__ void __launch_bounds__(kAttnThreads) relpos_bias_kernel(const AttnArg
     }
 }
 
+// ---------------------------------------------------------------- rel-pos bias, windowed blocks, one CTA per (window, head)
+// Stages the window's q rows and both relative tables in shared memory once, then each warp walks lines
+// (all tokens sharing ly, or sharing lx): a 16 x 16 x DH product per line with ldmatrix row gathers.
+// Output: combined tensor-core layout (Bw, H, 256, 64): columns [0, wh) = 8 bias_h, [wh, wh + ww) = 8 bias_w.
+template <typename T, int DH>
+__global__ void __launch_bounds__(kAttnThreads) relpos_window_kernel(const AttnArgs a, const T* rel_y, const T* rel_x, T* comb,
+                                                                      float scale) {
+    et_pdl_prologue();
+    constexpr int LD = DH + 8;
+    extern __shared__ __align__(16) uint8_t smraw[];
+    const int wh = a.wh, ww = a.ww, Wn = a.Wn;
+    T* Qs = reinterpret_cast<T*>(smraw);            // [Wn + 1][LD], last row = zeros
+    T* Ty = Qs + (Wn + 1) * LD;                     // [wh * wh + 1][LD]
+    T* Tx = Ty + (wh * wh + 1) * LD;                // [ww * ww + 1][LD]
+    const TokenMap map = make_map(a);
+    const int bw = blockIdx.x, h = blockIdx.y;
+    const int nwin = a.nwx * a.nwy;
+    const int b = bw / nwin, win = bw - b * nwin;
+    const int D = a.H * DH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    stage_rows<T, DH, LD>(Qs, Wn + 1, [&](int r) -> const T* {
+        if (r >= Wn) return nullptr;
+        const int tok = map.token(win, r);
+        return tok >= 0 ? static_cast<const T*>(a.qkv) + ((size_t)b * a.N + tok) * 3 * D + h * DH
+                        : static_cast<const T*>(a.pad_token) + h * DH;
+    });
+    stage_rows<T, DH, LD>(Ty, wh * wh + 1, [&](int r) -> const T* { return r < wh * wh ? rel_y + (size_t)r * DH : nullptr; });
+    stage_rows<T, DH, LD>(Tx, ww * ww + 1, [&](int r) -> const T* { return r < ww * ww ? rel_x + (size_t)r * DH : nullptr; });
+    cp_async_wait_all();
+    __syncthreads();
+    T* dst = comb + ((size_t)bw * a.H + h) * 256 * 64;
+    for (int line = warp; line < wh + ww; line += kAttnThreads / 32) {
+        const bool ymode = line < wh;
+        const int fixed = ymode ? line : line - wh;
+        const int ntok = ymode ? ww : wh, nout = ymode ? wh : ww;
+        const T* tab = ymode ? Ty : Tx;
+        const int tab_rows = ymode ? wh * wh : ww * ww;
+        for (int j0 = 0; j0 < ntok; j0 += 16) {
+            for (int o0 = 0; o0 < nout; o0 += 16) {
+                float acc[2][4] = {};
+#pragma unroll
+                for (int ks = 0; ks < DH / 16; ++ks) {
+                    uint32_t af[4], bf[4];
+                    const int j = j0 + (lane & 15);
+                    const int t = ymode ? fixed * ww + j : j * ww + fixed;
+                    ldsm_x4(af, Qs + (j < ntok ? t : Wn) * LD + ks * 16 + (lane >> 4) * 8);
+                    const int kc = o0 + (lane & 7) + (lane >> 4) * 8;
+                    ldsm_x4(bf, tab + (kc < nout ? fixed * nout + kc : tab_rows) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
+                    mma16816<T>(acc[0], af, bf[0], bf[1]);
+                    mma16816<T>(acc[1], af, bf[2], bf[3]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int j = j0 + g + (i >> 1) * 8;
+                        const int kc = o0 + nt * 8 + tq * 2 + (i & 1);
+                        if (j < ntok && kc < nout) {
+                            const int t = ymode ? fixed * ww + j : j * ww + fixed;
+                            dst[(size_t)t * 64 + (ymode ? 0 : wh) + kc] = ElemTraits<T>::from_float(acc[nt][i] * scale);
+                        }
+                    }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- windowed / small dense attention
 // grid (ceil(Wn / 64), H, B * n_windows)
 template <typename T, int DH>
 __global__ void __launch_bounds__(kAttnThreads) window_attention_kernel(const AttnArgs a) {
+    et_pdl_prologue();
     constexpr int LD = DH + 8;
     extern __shared__ __align__(16) uint8_t smraw[];
     T* Qs = reinterpret_cast<T*>(smraw);
@@ -382,6 +452,7 @@ __global__ void __launch_bounds__(kAttnThreads) window_attention_kernel(const At
 // grid (N / 64 rounded up, H, B): row max / row sum of the softmax over ALL keys.
 template <typename T, int DH>
 __global__ void __launch_bounds__(kAttnThreads) attn_stats_kernel(const AttnArgs a) {
+    et_pdl_prologue();
     constexpr int LD = DH + 8;
     extern __shared__ __align__(16) uint8_t smraw[];
     T* Qs = reinterpret_cast<T*>(smraw);
@@ -473,6 +544,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_stats_kernel(const AttnArgs
 // k gate-selected tokens (DELTA).  a_state is column-major per head: a_state[b][h][col][row].
 template <typename T, int DH, int MODE>
 __global__ void __launch_bounds__(kAttnThreads) attn_apply_kernel(const AttnArgs a) {
+    et_pdl_prologue();
     constexpr int LD = DH + 8;
     constexpr int LDP = BQ + 8;
     extern __shared__ __align__(16) uint8_t smraw[];
@@ -657,6 +729,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_apply_kernel(const AttnArgs
 template <typename T>
 __global__ void __launch_bounds__(256) vgate_kernel(const T* qkv, T* v_state, const long long* idx, T* Ksel, T* dV, T* Vd,
                                                     int N, int D, int k, long long total_vec, int emit_vn) {
+    et_pdl_prologue();
     const int nch = D / 8;
     for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total_vec;
          gi += (long long)gridDim.x * blockDim.x) {
@@ -725,8 +798,10 @@ int run_window(const AttnArgs& a, const void* rel_y, const void* rel_x, void* bi
             T* comb = static_cast<T*>(bias_ws);
             const size_t bytes = (size_t)a.B * nwin * a.H * 256 * 64 * sizeof(T);
             if (cudaMemsetAsync(comb, 0, bytes, s) != cudaSuccess) return et_fail(ET_ERR_CUDA, "cudaMemsetAsync failed");
-            relpos_bias_kernel<T, DH><<<dim3(lh + lw, a.H, a.B * nwin), kAttnThreads, 0, s>>>(
-                a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), comb, comb, 64, 8.f, 256, 1);
+            const int smem_rp = ((a.Wn + 1) + (lh * lh + 1) + (lw * lw + 1)) * (DH + 8) * (int)sizeof(T) + 16;
+            int rc = set_smem(relpos_window_kernel<T, DH>, smem_rp);
+            if (rc) return rc;
+            et_launch(relpos_window_kernel<T, DH>, dim3(dim3(a.B * nwin, a.H)), dim3(kAttnThreads), smem_rp, s, a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), comb, 8.f);
             ET_COUNT_LAUNCH(1);
         }
         return et_tc_window_attention(a.qkv, a.pad_token, bias_ws, a.out, a.B, a.N, a.gh, a.gw, a.wh, a.ww, a.H,
@@ -735,8 +810,7 @@ int run_window(const AttnArgs& a, const void* rel_y, const void* rel_x, void* bi
     if (rel_y != nullptr) {
         T* bh = static_cast<T*>(bias_ws);
         T* bw = bh + align8((size_t)a.B * nwin * a.H * a.Wn * lh);
-        relpos_bias_kernel<T, DH><<<dim3(lh + lw, a.H, a.B * nwin), kAttnThreads, 0, s>>>(
-            a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw, 0, 1.f, 0, 0);
+        et_launch(relpos_bias_kernel<T, DH>, dim3(dim3(lh + lw, a.H, a.B * nwin)), dim3(kAttnThreads), 0, s, a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw, 0, 1.f, 0, 0);
         ET_COUNT_LAUNCH(1);
         args.bias_h = bh;
         args.bias_w = bw;
@@ -744,7 +818,7 @@ int run_window(const AttnArgs& a, const void* rel_y, const void* rel_x, void* bi
     const int smem = (BQ * (DH + 8) + 2 * BKV * (DH + 8) + BQ * (lh + 1 + lw + 1)) * (int)sizeof(T) + 16;
     int rc = set_smem(window_attention_kernel<T, DH>, smem);
     if (rc) return rc;
-    window_attention_kernel<T, DH><<<dim3((a.Wn + BQ - 1) / BQ, a.H, a.B * nwin), kAttnThreads, smem, s>>>(args);
+    et_launch(window_attention_kernel<T, DH>, dim3(dim3((a.Wn + BQ - 1) / BQ, a.H, a.B * nwin)), dim3(kAttnThreads), smem, s, args);
     ET_COUNT_LAUNCH(1);
     return ET_OK;
 }
@@ -764,8 +838,7 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     T* Vd = dV + (size_t)a.B * a.k * D;
     T* onehot = Vd + (size_t)a.B * a.k * D;
     if (rel_y != nullptr) {
-        relpos_bias_kernel<T, DH><<<dim3(a.gh + a.gw, a.H, a.B), kAttnThreads, 0, s>>>(
-            a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw, use_tc ? 64 : 0, use_tc ? 8.f : 1.f, 0, 0);
+        et_launch(relpos_bias_kernel<T, DH>, dim3(dim3(a.gh + a.gw, a.H, a.B)), dim3(kAttnThreads), 0, s, a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw, use_tc ? 64 : 0, use_tc ? 8.f : 1.f, 0, 0);
         ET_COUNT_LAUNCH(1);
         args.bias_h = bh;
         args.bias_w = bw;
@@ -774,7 +847,7 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     if (a.mode == ET_ATTN_DELTA) {
         const long long total = (long long)a.B * a.k * (D / 8);
         if (total > 0)
-            vgate_kernel<T><<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, static_cast<T*>(v_state), a.idx,
+            et_launch(vgate_kernel<T>, dim3((int)((total + 255) / 256)), dim3(256), 0, s, qkv, static_cast<T*>(v_state), a.idx,
                                                                       use_tc ? Ksel : nullptr, dV, Vd, a.N, D, a.k, total,
                                                                       use_tc ? 1 : 0);
         ET_COUNT_LAUNCH(1);
@@ -782,7 +855,7 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
         args.Vd = Vd;
     } else if (a.mode == ET_ATTN_FIRST) {
         const long long total = (long long)a.B * a.N * (D / 8);
-        vgate_kernel<T><<<(int)((total + 255) / 256), 256, 0, s>>>(qkv, static_cast<T*>(v_state), nullptr, nullptr, nullptr,
+        et_launch(vgate_kernel<T>, dim3((int)((total + 255) / 256)), dim3(256), 0, s, qkv, static_cast<T*>(v_state), nullptr, nullptr, nullptr,
                                                                   nullptr, a.N, D, a.N, total, 0);
         ET_COUNT_LAUNCH(1);
     }
@@ -795,20 +868,20 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     const int smem_a = (BQ * (DH + 8) + BKV * (DH + 8) + BQ * (a.gh + 1 + a.gw + 1)) * (int)sizeof(T) + 16;
     int rc = set_smem(attn_stats_kernel<T, DH>, smem_a);
     if (rc) return rc;
-    attn_stats_kernel<T, DH><<<grid, kAttnThreads, smem_a, s>>>(args);
+    et_launch(attn_stats_kernel<T, DH>, dim3(grid), dim3(kAttnThreads), smem_a, s, args);
     ET_COUNT_LAUNCH(1);
     const int smem_b = apply_smem<T, DH>(a.gh, a.gw);
     if (a.mode == ET_ATTN_DELTA) {
         if ((rc = set_smem(attn_apply_kernel<T, DH, ET_ATTN_DELTA>, smem_b))) return rc;
-        if (a.k > 0) attn_apply_kernel<T, DH, ET_ATTN_DELTA><<<grid, kAttnThreads, smem_b, s>>>(args);
+        if (a.k > 0) et_launch(attn_apply_kernel<T, DH, ET_ATTN_DELTA>, dim3(grid), dim3(kAttnThreads), smem_b, s, args);
         ET_COUNT_LAUNCH(1);
     } else if (a.mode == ET_ATTN_FIRST) {
         if ((rc = set_smem(attn_apply_kernel<T, DH, ET_ATTN_FIRST>, smem_b))) return rc;
-        attn_apply_kernel<T, DH, ET_ATTN_FIRST><<<grid, kAttnThreads, smem_b, s>>>(args);
+        et_launch(attn_apply_kernel<T, DH, ET_ATTN_FIRST>, dim3(grid), dim3(kAttnThreads), smem_b, s, args);
         ET_COUNT_LAUNCH(1);
     } else {
         if ((rc = set_smem(attn_apply_kernel<T, DH, ET_ATTN_DENSE>, smem_b))) return rc;
-        attn_apply_kernel<T, DH, ET_ATTN_DENSE><<<grid, kAttnThreads, smem_b, s>>>(args);
+        et_launch(attn_apply_kernel<T, DH, ET_ATTN_DENSE>, dim3(grid), dim3(kAttnThreads), smem_b, s, args);
         ET_COUNT_LAUNCH(1);
     }
     return ET_OK;

@@ -71,6 +71,7 @@ constexpr int ST_SMEM = ST_OFF_X + QROWS * 8 + 256 + 1024;
 
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const TcArgs a) {
+    et_pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Qs = smem;
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                 const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bw,
                 const __grid_constant__ CUtensorMap tm_oh, const TcArgs a) {
+    et_pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     auto Qb = [&](int i) { return smem + i * QROWS * 128; };
@@ -543,6 +545,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // One-hot key coordinates for the augmented K operand: row j = [onehot(ky_j) (64) | onehot(kx_j) (64)].
 template <bool BF16>
 __global__ void __launch_bounds__(256) onehot_kernel(const long long* idx, uint16_t* oh, int rows, int gw) {
+    et_pdl_prologue();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk (8 columns) per thread
     if (g >= rows * 16) return;
     const int j = g >> 4, chunk = g & 15;
@@ -585,20 +588,20 @@ int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, i
         if ((rc = make_tmap_2d(&tmbh, a.bias_h, brows, 64, 128, a.is_bf16))) return rc;
         if ((rc = make_tmap_2d(&tmbw, a.bias_w, brows, 64, 128, a.is_bf16))) return rc;
         if ((rc = make_tmap_2d(&tmoh, onehot, oh_rows, 128, 64, a.is_bf16))) return rc;
-        onehot_kernel<BF16><<<(oh_rows * 16 + 255) / 256, 256, 0, s>>>(mode == ET_ATTN_DELTA ? a.idx : nullptr,
+        et_launch(onehot_kernel<BF16>, dim3((oh_rows * 16 + 255) / 256), dim3(256), 0, s, mode == ET_ATTN_DELTA ? a.idx : nullptr,
                                                                         static_cast<uint16_t*>(onehot), oh_rows, a.gw);
         ET_COUNT_LAUNCH(1);
     }
     const dim3 grid(a.N / QROWS, a.H, a.B);
-    tc_stats_kernel<BF16><<<grid, kThreads, ST_SMEM, s>>>(tm128, a);
+    et_launch(tc_stats_kernel<BF16>, dim3(grid), dim3(kThreads), ST_SMEM, s, tm128, a);
     ET_COUNT_LAUNCH(1);
     if (mode == ET_ATTN_DELTA) {
         if ((rc = make_tmap_2d(&tmsel, sel, 3LL * a.sel_rows, (long long)a.D, 64, a.is_bf16))) return rc;
-        tc_apply_kernel<BF16, ET_ATTN_DELTA><<<grid, kThreads, AP_SMEM, s>>>(tm128, tmsel, tmbh, tmbw, tmoh, a);
+        et_launch(tc_apply_kernel<BF16, ET_ATTN_DELTA>, dim3(grid), dim3(kThreads), AP_SMEM, s, tm128, tmsel, tmbh, tmbw, tmoh, a);
     } else if (mode == ET_ATTN_FIRST) {
-        tc_apply_kernel<BF16, ET_ATTN_FIRST><<<grid, kThreads, AP_SMEM, s>>>(tm128, tm64, tmbh, tmbw, tmoh, a);
+        et_launch(tc_apply_kernel<BF16, ET_ATTN_FIRST>, dim3(grid), dim3(kThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
     } else {
-        tc_apply_kernel<BF16, ET_ATTN_DENSE><<<grid, kThreads, AP_SMEM, s>>>(tm128, tm64, tmbh, tmbw, tmoh, a);
+        et_launch(tc_apply_kernel<BF16, ET_ATTN_DENSE>, dim3(grid), dim3(kThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
     }
     ET_COUNT_LAUNCH(1);
     return ET_OK;

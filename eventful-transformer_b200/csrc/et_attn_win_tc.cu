@@ -63,6 +63,7 @@ template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_window_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_bias,
                  const __grid_constant__ CUtensorMap tm_oh, const WinArgs a) {
+    et_pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Qq = smem;
@@ -265,6 +266,7 @@ tc_window_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 // K' one-hot block of a (wh x ww) window: row j -> column (j / ww) and column wh + (j % ww); 256 rows x 64 columns.
 template <bool BF16>
 __global__ void __launch_bounds__(256) window_onehot_kernel(uint16_t* oh, int wh, int ww) {
+    et_pdl_prologue();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk per thread: 256 rows x 8 chunks
     if (g >= 256 * 8) return;
     const int j = g >> 3, chunk = g & 7;
@@ -322,13 +324,13 @@ int et_tc_window_attention(const void* qkv, const void* pad_token, void* bias_co
         uint16_t* oh = static_cast<uint16_t*>(bias_comb) + (size_t)B * nwin * H * 256 * 64;
         if ((rc = make_tmap_2d(&tb, bias_comb, (long long)B * nwin * H * 256, 64, 128, is_bf16))) return rc;
         if ((rc = make_tmap_2d(&toh, oh, 256, 64, a.NK, is_bf16))) return rc;
-        if (is_bf16) window_onehot_kernel<true><<<8, 256, 0, s>>>(oh, wh, ww);
-        else window_onehot_kernel<false><<<8, 256, 0, s>>>(oh, wh, ww);
+        if (is_bf16) et_launch(window_onehot_kernel<true>, dim3(8), dim3(256), 0, s, oh, wh, ww);
+        else et_launch(window_onehot_kernel<false>, dim3(8), dim3(256), 0, s, oh, wh, ww);
         ET_COUNT_LAUNCH(1);
     }
     const dim3 grid(B * nwin, H);
-    if (is_bf16) tc_window_kernel<true><<<grid, kThreads, W_SMEM, s>>>(tq, tb, toh, a);
-    else tc_window_kernel<false><<<grid, kThreads, W_SMEM, s>>>(tq, tb, toh, a);
+    if (is_bf16) et_launch(tc_window_kernel<true>, dim3(grid), dim3(kThreads), W_SMEM, s, tq, tb, toh, a);
+    else et_launch(tc_window_kernel<false>, dim3(grid), dim3(kThreads), W_SMEM, s, tq, tb, toh, a);
     ET_COUNT_LAUNCH(1);
     return ET_OK;
 }

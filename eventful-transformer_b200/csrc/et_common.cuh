@@ -124,6 +124,32 @@ __device__ __forceinline__ float group_sum(float v) {
 
 static inline cudaStream_t et_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel begins with et_pdl_prologue(): it lets the NEXT kernel in the stream start launching right away and
+// then waits until the PREVIOUS kernel has completed and flushed its writes.  Every launch goes through et_launch(),
+// which sets cudaLaunchAttributeProgrammaticStreamSerialization, so launch latency and CTA scheduling of kernel n+1
+// overlap the tail of kernel n.  Opt-in with EVENTFUL_B200_PDL=1: measured on B200 it gains nothing under CUDA-graph
+// replay (265 vs 273 frames/s), where launches are already back to back.
+__device__ __forceinline__ void et_pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+extern int g_et_pdl;
+template <typename... KArgs, typename... Args>
+inline void et_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_et_pdl;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through ET_CHECK_LAUNCH
+}
+
 // Number of kernels this library has enqueued (bench.py reports it as gpu_launches).
 extern long long g_et_launches;
 #define ET_COUNT_LAUNCH(n) (g_et_launches += (n))

@@ -7,10 +7,13 @@
 //   gate_gather_kernel  : c~ = c[idx] (LayerNorm recomputed in registers), e~, p[idx] = c~
 //   buffer_scatter      : TokenBuffer row / column scatter
 //   add                 : residual add
+#include <cstdlib>
+
 #include "et_common.cuh"
 
 thread_local char g_et_error[512] = "";
 long long g_et_launches = 0;
+int g_et_pdl = []() { const char* e = getenv("EVENTFUL_B200_PDL"); return (e && e[0] == '1') ? 1 : 0; }();
 
 unsigned long long* g_gate_dbg = nullptr;  // et_debug_set(3, device pointer to 8 x u64) enables phase timestamps
 
@@ -275,6 +278,7 @@ __device__ __forceinline__ void select_row(const GateArgs& a, int r, int* s_hist
 
 template <typename T, int LPT, int CPL>
 __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArgs a) {
+    et_pdl_prologue();
     constexpr int VEC = ElemTraits<T>::VEC;
     constexpr int GROUPS = kGateThreads / LPT;
     __shared__ int s_hist[128];
@@ -377,6 +381,7 @@ struct GatherArgs {
 
 template <typename T, int LPT, int CPL>
 __global__ void __launch_bounds__(kGateThreads) gate_gather_kernel(const GatherArgs a) {
+    et_pdl_prologue();
     constexpr int VEC = ElemTraits<T>::VEC;
     constexpr int GROUPS = kGateThreads / LPT;
     const int lane = threadIdx.x % LPT;
@@ -433,6 +438,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_gather_kernel(const GatherA
 // p <- LN?(x) for every token (SimpleSTGTGate, modules.py:44) / plain vector copy
 template <typename T, int LPT, int CPL>
 __global__ void __launch_bounds__(kGateThreads) gate_replace_kernel(const GatherArgs a) {
+    et_pdl_prologue();
     constexpr int VEC = ElemTraits<T>::VEC;
     constexpr int GROUPS = kGateThreads / LPT;
     const int lane = threadIdx.x % LPT;
@@ -461,6 +467,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) scatter_rows_kernel(T* buf, const T* x, const long long* idx,
                                                            const int* count, int rows_per_index, int N, int D,
                                                            int k, long long total_vec) {
+    et_pdl_prologue();
     constexpr int VEC = ElemTraits<T>::VEC;
     const int nchunks = D / VEC;
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total_vec;
@@ -480,6 +487,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) scatter_cols_kernel(T* buf, const T* x, const long long* idx,
                                                            int rows_per_index, int N, int M, int k,
                                                            long long total) {
+    et_pdl_prologue();
     // buf (R, N, M), x (R, N, k): buf[r, n, idx[j]] = x[r, n, j]
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
          g += (long long)gridDim.x * blockDim.x) {
@@ -496,6 +504,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gather_cols_kernel(const T* c, T* p, const long long* idx,
                                                           int rows_per_index, int N, int M, int k, T* c_tilde,
                                                           T* e_tilde, long long total) {
+    et_pdl_prologue();
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
          g += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(g % k);
@@ -513,6 +522,7 @@ __global__ void __launch_bounds__(256) gather_cols_kernel(const T* c, T* p, cons
 
 template <typename T>
 __global__ void __launch_bounds__(256) add_kernel(const T* a, const T* b, T* out, long long nvec, float sign) {
+    et_pdl_prologue();
     constexpr int VEC = ElemTraits<T>::VEC;
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < nvec;
          g += (long long)gridDim.x * blockDim.x) {
@@ -552,7 +562,7 @@ int dispatch_row_shape(int D, Args&&... args) {
 template <typename T, int LPT, int CPL>
 struct SelectLauncher {
     static int run(const GateArgs& a, int ctas_per_row, int R, cudaStream_t s) {
-        gate_select_kernel<T, LPT, CPL><<<dim3(ctas_per_row, R), kGateThreads, 0, s>>>(a);
+        et_launch(gate_select_kernel<T, LPT, CPL>, dim3(dim3(ctas_per_row, R)), dim3(kGateThreads), 0, s, a);
         ET_COUNT_LAUNCH(1);
         return 0;
     }
@@ -561,7 +571,7 @@ template <typename T, int LPT, int CPL>
 struct GatherLauncher {
     static int run(const GatherArgs& a, cudaStream_t s) {
         constexpr int GROUPS = kGateThreads / LPT;
-        gate_gather_kernel<T, LPT, CPL><<<(a.total_rows + GROUPS - 1) / GROUPS, kGateThreads, 0, s>>>(a);
+        et_launch(gate_gather_kernel<T, LPT, CPL>, dim3((a.total_rows + GROUPS - 1) / GROUPS), dim3(kGateThreads), 0, s, a);
         ET_COUNT_LAUNCH(1);
         return 0;
     }
@@ -570,7 +580,7 @@ template <typename T, int LPT, int CPL>
 struct ReplaceLauncher {
     static int run(const GatherArgs& a, cudaStream_t s) {
         constexpr int GROUPS = kGateThreads / LPT;
-        gate_replace_kernel<T, LPT, CPL><<<(a.total_rows + GROUPS - 1) / GROUPS, kGateThreads, 0, s>>>(a);
+        et_launch(gate_replace_kernel<T, LPT, CPL>, dim3((a.total_rows + GROUPS - 1) / GROUPS), dim3(kGateThreads), 0, s, a);
         ET_COUNT_LAUNCH(1);
         return 0;
     }
@@ -689,8 +699,7 @@ int et_gate_gather_cols(const void* c, void* p, const int64_t* idx, int64_t R, i
     const long long total = (long long)R * N * k;
     if (total == 0) return ET_OK;
     ET_DISPATCH_DTYPE(dtype, T, {
-        gather_cols_kernel<T><<<grid_for(total, 256), 256, 0, et_stream(stream)>>>(
-            static_cast<const T*>(c), static_cast<T*>(p), reinterpret_cast<const long long*>(idx), (int)rows_per_index,
+        et_launch(gather_cols_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, et_stream(stream), static_cast<const T*>(c), static_cast<T*>(p), reinterpret_cast<const long long*>(idx), (int)rows_per_index,
             (int)N, (int)M, (int)k, static_cast<T*>(c_tilde), static_cast<T*>(e_tilde), total);
     });
     ET_COUNT_LAUNCH(1);
@@ -710,14 +719,12 @@ int et_buffer_scatter(void* buf, const void* x, const int64_t* idx, const int32_
             ET_CHECK_ARG(D % VEC == 0 && et_aligned16(buf) && et_aligned16(x),
                          "et_buffer_scatter: rows must be 16-byte multiples and aligned");
             const long long total = (long long)R * k * (D / VEC);
-            scatter_rows_kernel<T><<<grid_for(total, 256), 256, 0, et_stream(stream)>>>(
-                static_cast<T*>(buf), static_cast<const T*>(x), reinterpret_cast<const long long*>(idx), count,
+            et_launch(scatter_rows_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, et_stream(stream), static_cast<T*>(buf), static_cast<const T*>(x), reinterpret_cast<const long long*>(idx), count,
                 (int)rows_per_index, (int)N, (int)D, (int)k, total);
         } else {
             ET_CHECK_ARG(count == nullptr, "et_buffer_scatter: device-side counts are row-structure only");
             const long long total = (long long)R * N * k;  // buf (R, N, D): D is the indexed axis
-            scatter_cols_kernel<T><<<grid_for(total, 256), 256, 0, et_stream(stream)>>>(
-                static_cast<T*>(buf), static_cast<const T*>(x), reinterpret_cast<const long long*>(idx),
+            et_launch(scatter_cols_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, et_stream(stream), static_cast<T*>(buf), static_cast<const T*>(x), reinterpret_cast<const long long*>(idx),
                 (int)rows_per_index, (int)N, (int)D, (int)k, total);
         }
     });
@@ -743,8 +750,7 @@ static int add_impl(const void* a, const void* b, void* out, int64_t n, int dtyp
     ET_DISPATCH_DTYPE(dtype, T, {
         constexpr int VEC = ElemTraits<T>::VEC;
         ET_CHECK_ARG(n % VEC == 0, "et_add: element count must be a multiple of %d", VEC);
-        add_kernel<T><<<grid_for(n / VEC, 256), 256, 0, et_stream(stream)>>>(
-            static_cast<const T*>(a), static_cast<const T*>(b), static_cast<T*>(out), n / VEC, sign);
+        et_launch(add_kernel<T>, dim3(grid_for(n / VEC, 256)), dim3(256), 0, et_stream(stream), static_cast<const T*>(a), static_cast<const T*>(b), static_cast<T*>(out), n / VEC, sign);
     });
     ET_COUNT_LAUNCH(1);
     ET_CHECK_LAUNCH("et_add");

@@ -46,6 +46,7 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                       const LinearArgs args) {
+    et_pdl_prologue();
     using L = GemmSmem<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
     extern __shared__ uint8_t smem_raw[];
@@ -196,12 +197,13 @@ int launch_linear(const void* A, const void* W, const LinearArgs& args, cudaStre
     rc = make_tmap_2d(&tw, W, args.n_feat, args.K, BLOCK_N, args.is_bf16);
     if (rc) return rc;
     dim3 grid((args.n_feat + BLOCK_N - 1) / BLOCK_N, (args.M + BLOCK_M - 1) / BLOCK_M);
-    linear_tcgen05_kernel<BLOCK_N, STAGES><<<grid, kGemmThreads, L::TOTAL, stream>>>(ta, tw, args);
+    et_launch(linear_tcgen05_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kGemmThreads), L::TOTAL, stream, ta, tw, args);
     ET_COUNT_LAUNCH(1);
     return ET_OK;
 }
 
-int g_force_block_n = 0;  // test hook: et_debug_set(1, BLOCK_N)
+int g_force_block_n = 0;
+int g_force_depth = 0;  // test / tuning hook: et_debug_set(5, 1 = deep pipelines, 2 = shallow (two CTAs per SM), 0 = auto)  // test hook: et_debug_set(1, BLOCK_N)
 
 }  // namespace
 
@@ -213,6 +215,10 @@ extern "C" {
 int et_debug_set(int key, long long value) {
     if (key == 1) {
         g_force_block_n = (int)value;
+        return ET_OK;
+    }
+    if (key == 5) {
+        g_force_depth = (int)value;
         return ET_OK;
     }
     if (key == 2) {
@@ -255,18 +261,24 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
         const int bn = candidates[c];
         if (bn > 64 && bn >= 2 * n_feat) continue;
         const long long tiles = mt * ((n_feat + bn - 1) / bn);
-        const double cost = (double)((tiles + 147) / 148) * (bn + 32);
+        const long long slots = tiles > 148 ? 296 : 148;  // two CTAs per SM with the shallow pipelines
+        const double cost = (double)((tiles + slots - 1) / slots) * (bn + 32) * (tiles > 148 ? 1.25 : 1.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
     }
     if (g_force_block_n) best = g_force_block_n;
     int rc;
     cudaStream_t s = et_stream(stream);
+    // Two pipeline depths per tile width: "deep" (one CTA per SM, longest TMA prefetch) and "shallow" (<= 110 KB of
+    // smem so two CTAs share an SM: the epilogue of one overlaps the mainloop of the other and a launch of up to 296
+    // tiles is a single wave).  Shallow is used when the tile count exceeds one CTA-per-SM wave.
+    const long long tiles_best = mt * ((n_feat + best - 1) / best);
+    const bool shallow = g_force_depth ? g_force_depth == 2 : tiles_best > 148;
     switch (best) {
-        case 256: rc = launch_linear<256, 4>(A, W, a, s); break;
-        case 192: rc = launch_linear<192, 5>(A, W, a, s); break;
-        case 128: rc = launch_linear<128, 6>(A, W, a, s); break;
-        case 96: rc = launch_linear<96, 7>(A, W, a, s); break;
-        case 64: rc = launch_linear<64, 8>(A, W, a, s); break;
+        case 256: rc = shallow ? launch_linear<256, 2>(A, W, a, s) : launch_linear<256, 4>(A, W, a, s); break;
+        case 192: rc = shallow ? launch_linear<192, 2>(A, W, a, s) : launch_linear<192, 5>(A, W, a, s); break;
+        case 128: rc = shallow ? launch_linear<128, 3>(A, W, a, s) : launch_linear<128, 6>(A, W, a, s); break;
+        case 96: rc = shallow ? launch_linear<96, 3>(A, W, a, s) : launch_linear<96, 7>(A, W, a, s); break;
+        case 64: rc = shallow ? launch_linear<64, 4>(A, W, a, s) : launch_linear<64, 8>(A, W, a, s); break;
         default: return et_fail(ET_ERR_ARG, "et_linear: unsupported BLOCK_N %d", best);
     }
     if (rc) return rc;

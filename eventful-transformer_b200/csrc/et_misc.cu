@@ -18,6 +18,7 @@ struct BmmArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(TILE * TILE) bmm_kernel(const BmmArgs a) {
+    et_pdl_prologue();
     __shared__ float As[TILE][TILE + 1];
     __shared__ float Bs[TILE][TILE + 1];
     const T* A = static_cast<const T*>(a.A) + (long long)blockIdx.z * a.sab;
@@ -57,7 +58,7 @@ extern "C" int et_bmm(const void* A, const void* Bm, void* C, int64_t batch, int
     a.accumulate = accumulate;
     const dim3 grid((unsigned)((N + TILE - 1) / TILE), (unsigned)((M + TILE - 1) / TILE), (unsigned)batch);
     ET_CHECK_ARG(grid.y <= 65535, "et_bmm: M too large");
-    ET_DISPATCH_DTYPE(dtype, T, { bmm_kernel<T><<<grid, TILE * TILE, 0, et_stream(stream)>>>(a); });
+    ET_DISPATCH_DTYPE(dtype, T, { et_launch(bmm_kernel<T>, dim3(grid), dim3(TILE * TILE), 0, et_stream(stream), a); });
     ET_COUNT_LAUNCH(1);
     ET_CHECK_LAUNCH("et_bmm");
     return ET_OK;
