@@ -297,11 +297,68 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
     T* xsum = static_cast<T*>(a.xsum);
     const T* p = static_cast<const T*>(a.p);
     const int iters = (a.tokens_per_cta + GROUPS - 1) / GROUPS;
-    // LayerNorm affine parameters: one copy per CTA in shared memory (overlaid on the key buffer, which is only
-    // used by the selection stage afterwards) instead of every warp re-reading the same L2 lines per token
     const T* ln_w = static_cast<const T*>(a.ln_w);
     const T* ln_b = static_cast<const T*>(a.ln_b);
-    if (ln_w != nullptr && (size_t)a.D * sizeof(T) * 2 <= sizeof(s_keys)) {
+    const bool stage_ln = ln_w != nullptr && (size_t)a.D * sizeof(T) * 2 <= sizeof(s_keys);
+
+    // Raw 16-byte chunks of one token (input, residual, reference state).  Two tokens per warp are kept in flight:
+    // all their loads (and the LayerNorm-parameter staging) are issued before the first reduction starts, so the
+    // phase is one DRAM round trip instead of a chain of three.
+    struct Raw {
+        uint4 xa[CPL], xb[CPL], p[CPL];
+    };
+    auto issue = [&](int it, Raw& rw) {
+        const int tok = t0 + it * GROUPS + group;
+        const bool valid = it < iters && tok < t1;
+        const size_t off = ((size_t)r * a.N + (valid ? tok : 0)) * a.D;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int ch = lane + c * LPT;
+            const bool on = valid && ch < nchunks;
+            rw.xa[c] = on ? ld_stream16(xa + off + (size_t)ch * VEC) : make_uint4(0, 0, 0, 0);
+            rw.xb[c] = (on && xb != nullptr) ? ld_stream16(xb + off + (size_t)ch * VEC) : make_uint4(0, 0, 0, 0);
+            rw.p[c] = (on && p != nullptr) ? ld_stream16(p + off + (size_t)ch * VEC) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    auto process = [&](int it, const Raw& rw) {
+        const int tok = t0 + it * GROUPS + group;
+        const bool valid = it < iters && tok < t1;
+        const size_t off = ((size_t)r * a.N + (valid ? tok : 0)) * a.D;
+        float v[CPL * VEC];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int ch = lane + c * LPT;
+            unpack16<T>(rw.xa[c], &v[c * VEC]);
+            if (xb != nullptr) {
+                float w[VEC];
+                unpack16<T>(rw.xb[c], w);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) v[c * VEC + i] = round_to<T>(v[c * VEC + i] + w[i]);
+                if (xsum != nullptr && valid && ch < nchunks) st16(xsum + off + (size_t)ch * VEC, pack16<T>(&v[c * VEC]));
+            }
+        }
+        if (ln_w != nullptr) layer_norm_row<T, LPT, CPL>(v, ln_w, ln_b, nchunks, lane, a.D, a.eps);
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            if (lane + c * LPT < nchunks) {
+                float q[VEC];
+                if (p != nullptr) unpack16<T>(rw.p[c], q);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float e = (p != nullptr) ? round_to<T>(v[c * VEC + i] - q[i]) : v[c * VEC + i];
+                    ss = fmaf(e, e, ss);
+                }
+            }
+        }
+        ss = group_sum<LPT>(ss);
+        if (valid && lane == 0) a.norm[(size_t)r * a.N + tok] = round_to<T>(sqrtf(ss));
+    };
+
+    Raw ra, rb;
+    issue(0, ra);
+    issue(1, rb);
+    if (stage_ln) {  // one copy of the LayerNorm affine parameters per CTA (overlaid on the key buffer of the selection stage)
         T* sw = reinterpret_cast<T*>(s_keys);
         T* sb = sw + a.D;
         for (int c = threadIdx.x; c < nchunks; c += kGateThreads) {
@@ -312,37 +369,11 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
         ln_w = sw;
         ln_b = sb;
     }
-
-    for (int it = 0; it < iters; ++it) {
-        const int tok = t0 + it * GROUPS + group;
-        const bool valid = tok < t1;
-        const size_t off = ((size_t)r * a.N + (valid ? tok : 0)) * a.D;
-        float v[CPL * VEC];
-        uint4 pv[CPL];
-        if (p != nullptr) {  // issue the reference-state loads together with the input loads
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const int ch = lane + c * LPT;
-                pv[c] = (valid && ch < nchunks) ? ld_stream16(p + off + (size_t)ch * VEC) : make_uint4(0, 0, 0, 0);
-            }
-        }
-        load_row<T, LPT, CPL>(xa, xb, xsum, off, nchunks, lane, valid, v);
-        if (ln_w != nullptr) layer_norm_row<T, LPT, CPL>(v, ln_w, ln_b, nchunks, lane, a.D, a.eps);
-        float ss = 0.f;
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            if (lane + c * LPT < nchunks) {
-                float q[VEC];
-                if (p != nullptr) unpack16<T>(pv[c], q);
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const float e = (p != nullptr) ? round_to<T>(v[c * VEC + i] - q[i]) : v[c * VEC + i];
-                    ss = fmaf(e, e, ss);
-                }
-            }
-        }
-        ss = group_sum<LPT>(ss);
-        if (valid && lane == 0) a.norm[(size_t)r * a.N + tok] = round_to<T>(sqrtf(ss));
+    for (int it = 0; it < iters; it += 2) {
+        process(it, ra);
+        if (it + 2 < iters) issue(it + 2, ra);
+        process(it + 1, rb);
+        if (it + 3 < iters) issue(it + 3, rb);
     }
 
     if (a.dbg != nullptr && threadIdx.x == 0) atomicMax(a.dbg + 1, gtime());
