@@ -31,6 +31,11 @@
 
 using namespace et_tc;
 
+// et_debug_set(6, 1): bracket the apply-kernel launch with CUDA events on its stream (bench.py reads the elapsed time
+// of the last launch through et_debug_elapsed_ms()); never enabled inside graph capture.
+int g_tc_time_apply = 0;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+
 namespace {
 
 constexpr int kThreads = 320;
@@ -595,6 +600,13 @@ int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, i
     const dim3 grid(a.N / QROWS, a.H, a.B);
     et_launch(tc_stats_kernel<BF16>, dim3(grid), dim3(kThreads), ST_SMEM, s, tm128, a);
     ET_COUNT_LAUNCH(1);
+    if (g_tc_time_apply) {
+        if (g_ev0 == nullptr) {
+            cudaEventCreate(&g_ev0);
+            cudaEventCreate(&g_ev1);
+        }
+        cudaEventRecord(g_ev0, s);
+    }
     if (mode == ET_ATTN_DELTA) {
         if ((rc = make_tmap_2d(&tmsel, sel, 3LL * a.sel_rows, (long long)a.D, 64, a.is_bf16))) return rc;
         et_launch(tc_apply_kernel<BF16, ET_ATTN_DELTA>, dim3(grid), dim3(kThreads), AP_SMEM, s, tm128, tmsel, tmbh, tmbw, tmoh, a);
@@ -604,10 +616,17 @@ int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, i
         et_launch(tc_apply_kernel<BF16, ET_ATTN_DENSE>, dim3(grid), dim3(kThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
     }
     ET_COUNT_LAUNCH(1);
+    if (g_tc_time_apply) cudaEventRecord(g_ev1, s);
     return ET_OK;
 }
 
 }  // namespace
+
+extern "C" float et_debug_elapsed_ms(void) {
+    float ms = -1.f;
+    if (g_ev1 != nullptr && cudaEventSynchronize(g_ev1) == cudaSuccess) cudaEventElapsedTime(&ms, g_ev0, g_ev1);
+    return ms;
+}
 
 // Entry used by et_global_attention (et_attn.cu) when the shape qualifies for the tensor-core path.
 // `sel` = workspace rows [K_sel | v_n | v_n - dV], each (B * k, D); `onehot` = (max(B * k, N), 128) scratch;

@@ -209,12 +209,17 @@ int g_force_depth = 0;  // test / tuning hook: et_debug_set(5, 1 = deep pipeline
 
 extern int g_attn_tc;
 extern unsigned long long* g_gate_dbg;
+extern int g_tc_time_apply;
 
 extern "C" {
 
 int et_debug_set(int key, long long value) {
     if (key == 1) {
         g_force_block_n = (int)value;
+        return ET_OK;
+    }
+    if (key == 6) {
+        g_tc_time_apply = (int)value;
         return ET_OK;
     }
     if (key == 5) {

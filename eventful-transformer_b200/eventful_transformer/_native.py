@@ -41,6 +41,7 @@ _SIGNATURES = {
     "et_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "et_sub": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "et_debug_set": (c_int, [c_int, c_longlong]),
+    "et_debug_elapsed_ms": (c_float, []),
     "et_linear": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64,
                           c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "et_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,

@@ -95,9 +95,13 @@ int et_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* 
 /* e = c - p (modules.py:149) for the generic (user-defined policy) gate path. */
 int et_sub(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
 
-/* Test / tuning hook: key 1 forces the GEMM tile width BLOCK_N (0 = automatic); key 2 = 0 routes global
- * attention through the mma.sync kernels even where the tcgen05 kernels apply (1 = default). */
+/* Test / tuning / measurement hooks.  key 1: force the GEMM tile width BLOCK_N (0 = automatic); key 2: 0 routes
+ * attention through the mma.sync kernels even where the tcgen05 kernels apply (1 = default); key 3: device pointer to
+ * 8 x uint64 receiving %globaltimer phase stamps of et_gate_select (0 = off); key 5: GEMM pipeline depth (1 deep,
+ * 2 shallow = two CTAs per SM, 0 = automatic); key 6: 1 brackets the global-attention apply kernel with CUDA events. */
 int et_debug_set(int key, long long value);
+/* Milliseconds of the last apply-kernel launch bracketed under key 6 (synchronises on its end event). */
+float et_debug_elapsed_ms(void);
 
 /*
  * Gathered-row linear with scatter epilogue on tcgen05 tensor cores (TMA operand
