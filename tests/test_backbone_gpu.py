@@ -108,3 +108,25 @@ def test_reset_restarts_the_stream_and_full_refresh_tracks_dense():
     with torch.inference_mode():
         again = m_full(frames[0].to(DT).to(DEV)).float().cpu()
     assert torch.equal(again, out_full[0])
+
+
+def test_frame_pipeline_overlapped_copies_match_direct_calls():
+    """et_pipeline.FramePipeline (upload / compute / download on two streams) returns exactly the direct results."""
+    import et_pipeline
+
+    case = dict(CASES["small_vitdet_b"], frames=6)
+    params, frames = case_params(case), case_frames(case)
+    _, direct, _ = run_gpu(case, params, frames)
+    model = build_gpu_backbone(case, params, DT)
+    host = [f.to(DT).pin_memory() for f in frames]
+    pipe = et_pipeline.FramePipeline(model, tuple(host[0].shape), DT, torch.device(DEV))
+    got = []
+    with torch.inference_mode():
+        for t, f in enumerate(host):
+            prev = pipe.step(f, host[t + 1] if t + 1 < len(host) else None)
+            if prev is not None:
+                got.append(prev.float().clone())
+        got.append(pipe.flush().float().clone())
+    assert len(got) == len(direct)
+    for a, b in zip(got, direct):
+        assert torch.equal(a, b)
