@@ -24,9 +24,10 @@
 //                                    V tiles are MN-major B operands straight from TMA.
 //                               epilogue: acc += O; out = acc.
 //                    FIRST / DENSE modes run the same pipeline over all keys with V from the QKV buffer.
-// Warp roles (320 threads): warp 0 = TMA / cp.async producer + state write-back, warp 1 = TMEM allocator and
-// single-thread MMA issuer, warps 2-9 = softmax / gate / epilogue: two warps per TMEM lane quarter, each thread
-// owns one query row and half of the tile's key columns.
+// Warp roles.  tc_stats (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator and single-thread MMA issuer,
+// warps 2-9 = softmax: two warps per TMEM lane quarter, each thread owns one query row and half of the tile's key
+// columns.  tc_apply (448 threads): the same plus four state-mover warps (2, 3, 12, 13) that own all A-gate state
+// traffic; its softmax / epilogue warps are 4-11.
 #include "et_tcgen05.cuh"
 
 using namespace et_tc;
@@ -34,6 +35,18 @@ using namespace et_tc;
 // et_debug_set(6, 1): bracket the apply-kernel launch with CUDA events on its stream (bench.py reads the elapsed time
 // of the last launch through et_debug_elapsed_ms()); never enabled inside graph capture.
 int g_tc_time_apply = 0;
+// et_debug_set(4, device pointer to 4 x 16 u64): per-role cycle buckets of tc_apply_kernel, summed over all CTAs.
+// Only the profiling build (make prof: -DET_TC_PROFILE -> libeventful_b200_prof.so) writes to it.
+unsigned long long* g_tc_prof = nullptr;
+#ifdef ET_TC_PROFILE
+#define PF_DECL long long pf_[16]; for (int i_ = 0; i_ < 16; ++i_) pf_[i_] = 0; long long pf_t_ = clock64();
+#define PF(i) do { const long long n_ = clock64(); pf_[i] += n_ - pf_t_; pf_t_ = n_; } while (0)
+#define PF_FLUSH(role) do { if (a.prof) for (int i_ = 0; i_ < 16; ++i_) atomicAdd(a.prof + (role) * 16 + i_, (unsigned long long)pf_[i_]); } while (0)
+#else
+#define PF_DECL
+#define PF(i)
+#define PF_FLUSH(role)
+#endif
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 
 namespace {
@@ -52,6 +65,7 @@ struct TcArgs {
     void* out;
     int B, N, NP, H, D, gh, gw, k, is_bf16, sel_rows, has_bias;
     float c1;  // (1 / sqrt(dh)) * log2(e)
+    unsigned long long* prof;
 };
 
 template <bool BF16>
@@ -233,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
 }
 
 // ============================================================================================= phase B
+constexpr int kApThreads = 448;  // warp 0 TMA, 1 MMA, 2-3 + 12-13 state movers, 4-11 softmax
 constexpr int AP_KEYS = 64;
 constexpr int AP_BLK = AP_KEYS * 64 * 2;          // 8 KB: one 64-key x 64-column operand block
 constexpr int AP_STAGE = 5 * AP_BLK;              // K, onehot-y, onehot-x, V1, V2
@@ -240,13 +255,13 @@ constexpr int AP_PT = AP_KEYS * QROWS * 2;        // 16 KB: a_state tile [key][r
 constexpr int AP_P = QROWS * AP_KEYS * 2;         // 16 KB: a_n tile (A operand, MN-major) = write-back staging
 constexpr int AP_OFF_ST = 3 * QROWS * 128;        // Q' = three 16 KB blocks: q, 8 bias_h, 8 bias_w
 constexpr int AP_OFF_PT = AP_OFF_ST + 2 * AP_STAGE;
-constexpr int AP_PT_STAGES = 3;                   // a_state tiles are prefetched three tiles ahead by the softmax threads
+constexpr int AP_PT_STAGES = 4;                   // a_state tiles are prefetched four tiles ahead by the mover warps
 constexpr int AP_OFF_P = AP_OFF_PT + AP_PT_STAGES * AP_PT;
 constexpr int AP_OFF_MISC = AP_OFF_P + AP_P;
 constexpr int AP_SMEM = AP_OFF_MISC + 1024 + 1024;
 
 template <bool BF16, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kApThreads, 1)
 tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                 const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bw,
                 const __grid_constant__ CUtensorMap tm_oh, const TcArgs a) {
@@ -262,17 +277,19 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     auto Pt = [&](int u) { return smem + AP_OFF_PT + u * AP_PT; };
     uint8_t* An = smem + AP_OFF_P;
     auto a_chunk = [](int key, int seg) { return (seg >> 3) * 8192 + key * 128 + (((seg & 7) ^ (key & 7)) << 4); };
-    int* s_tok = reinterpret_cast<int*>(smem + AP_OFF_MISC);  // [2][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AP_OFF_MISC + 512);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;
-    uint64_t* ps_full = bars + 3;   // [3]: a_state tile landed (256 cp.async arrivals, one per softmax thread)
-    uint64_t* s_full = bars + 6;
-    uint64_t* s_empty = bars + 8;
-    uint64_t* p_ready = bars + 10;  // single P buffer: one barrier, one phase per tile
-    uint64_t* pv_done = bars + 11;  // [2]: PV MMAs of tile t commit to slot t & 1 (at most one phase outstanding each)
-    uint64_t* o_full = bars + 13;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* k_full = bars + 1;    // [2]: K' operand blocks of a stage landed
+    uint64_t* ps_full = bars + 3;   // [4]: a_state tile landed (128 cp.async arrivals, one per mover thread)
+    uint64_t* s_full = bars + 7;
+    uint64_t* s_empty = bars + 9;
+    uint64_t* p_ready = bars + 11;  // single a_n buffer: one barrier, one phase per tile (8 softmax warps arrive)
+    uint64_t* pv_done = bars + 12;  // [2]: PV MMAs of tile t commit to slot t & 1 (at most one phase outstanding each)
+    uint64_t* o_full = bars + 14;
+    uint64_t* an_free = bars + 15;  // a_n tile copied out by the 4 mover warps, one phase per tile
+    uint64_t* v_full = bars + 16;   // [2]: V blocks of a stage landed (released by pv_done)
+    uint64_t* k_empty = bars + 18;  // [2]: S' MMAs of the stage's tile are complete -> its K' blocks may be reloaded
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * QROWS, h = blockIdx.y, b = blockIdx.z;
@@ -288,13 +305,16 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_init(smem_u32(q_full), 1);
         mbar_init(smem_u32(o_full), 1);
         mbar_init(smem_u32(p_ready), 8);
+        mbar_init(smem_u32(an_free), 4);
         for (int u = 0; u < 2; ++u) {
-            mbar_init(smem_u32(&kv_full[u]), 1);
+            mbar_init(smem_u32(&k_full[u]), 1);
+            mbar_init(smem_u32(&v_full[u]), 1);
+            mbar_init(smem_u32(&k_empty[u]), 1);
             mbar_init(smem_u32(&s_full[u]), 1);
             mbar_init(smem_u32(&s_empty[u]), 8);
             mbar_init(smem_u32(&pv_done[u]), 1);
         }
-        for (int u = 0; u < AP_PT_STAGES; ++u) mbar_init(smem_u32(&ps_full[u]), 256);
+        for (int u = 0; u < AP_PT_STAGES; ++u) mbar_init(smem_u32(&ps_full[u]), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
@@ -316,37 +336,46 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tma_load_2d(smem_u32(Qb(2)), &tm_bw, smem_u32(q_full), 0, brow);
             }
         }
-        for (int t = 0; t < T; ++t) {
-            const int u = t & 1, key0 = t * AP_KEYS;
-            if (t >= 2) mbar_wait(smem_u32(&pv_done[u]), ((t >> 1) & 1) ^ 1);  // tile t-2: the MMAs are done with slot u
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int j = key0 + lane + half * 32;
-                int tok = -1;
-                if (j < nkeys) tok = (MODE == ET_ATTN_DELTA) ? (int)a.idx[(size_t)b * a.k + j] : j;
-                s_tok[u * AP_KEYS + lane + half * 32] = tok;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                const uint32_t fb = smem_u32(&kv_full[u]);
-                const int nblk = nkb + (MODE == ET_ATTN_DELTA ? 2 : 1);
-                mbar_expect_tx(fb, nblk * AP_BLK);
-                const int orow = (MODE == ET_ATTN_DELTA) ? b * a.k + key0 : key0;
-                if (MODE == ET_ATTN_DELTA) {
-                    const int r0 = b * a.k + key0;
-                    tma_load_2d(smem_u32(Kb(u, 0)), &tm_kv, fb, h * 64, r0);
-                    tma_load_2d(smem_u32(V1(u)), &tm_kv, fb, h * 64, a.sel_rows + r0);
-                    tma_load_2d(smem_u32(V2(u)), &tm_kv, fb, h * 64, 2 * a.sel_rows + r0);
-                } else {
-                    tma_load_2d(smem_u32(Kb(u, 0)), &tm_kv, fb, a.D + h * 64, b * a.N + key0);
-                    tma_load_2d(smem_u32(V1(u)), &tm_kv, fb, 2 * a.D + h * 64, b * a.N + key0);
+        // K' blocks and V blocks of a stage are separate transactions: K'(t) is reloadable as soon as S'(t-2) has been
+        // computed (a full tile before the PV MMAs of t-2 finish), so the S' MMAs - which run one tile ahead of the PV
+        // MMAs - never wait for the TMA round trip.  Issue order: K'(0) K'(1) V(0) K'(2) V(1) ...
+        PF_DECL
+        if (lane == 0) {
+            for (int i = 0; i <= T; ++i) {
+                if (i < T) {
+                    const int u = i & 1, key0 = i * AP_KEYS;
+                    PF(1);
+                    if (i >= 2) mbar_wait(smem_u32(&k_empty[u]), ((i >> 1) & 1) ^ 1);
+                    PF(0);
+                    const uint32_t fb = smem_u32(&k_full[u]);
+                    mbar_expect_tx(fb, nkb * AP_BLK);
+                    if (MODE == ET_ATTN_DELTA) tma_load_2d(smem_u32(Kb(u, 0)), &tm_kv, fb, h * 64, b * a.k + key0);
+                    else tma_load_2d(smem_u32(Kb(u, 0)), &tm_kv, fb, a.D + h * 64, b * a.N + key0);
+                    if (a.has_bias) {
+                        const int orow = (MODE == ET_ATTN_DELTA) ? b * a.k + key0 : key0;
+                        tma_load_2d(smem_u32(Kb(u, 1)), &tm_oh, fb, 0, orow);
+                        tma_load_2d(smem_u32(Kb(u, 2)), &tm_oh, fb, 64, orow);
+                    }
                 }
-                if (a.has_bias) {
-                    tma_load_2d(smem_u32(Kb(u, 1)), &tm_oh, fb, 0, orow);
-                    tma_load_2d(smem_u32(Kb(u, 2)), &tm_oh, fb, 64, orow);
+                if (i >= 1) {
+                    const int j = i - 1, u = j & 1, key0 = j * AP_KEYS;
+                    PF(1);
+                    if (j >= 2) mbar_wait(smem_u32(&pv_done[u]), ((j >> 1) & 1) ^ 1);  // tile j-2: the PV MMAs are done with slot u
+                    PF(2);
+                    const uint32_t fb = smem_u32(&v_full[u]);
+                    mbar_expect_tx(fb, (MODE == ET_ATTN_DELTA ? 2 : 1) * AP_BLK);
+                    if (MODE == ET_ATTN_DELTA) {
+                        const int r0 = b * a.k + key0;
+                        tma_load_2d(smem_u32(V1(u)), &tm_kv, fb, h * 64, a.sel_rows + r0);
+                        tma_load_2d(smem_u32(V2(u)), &tm_kv, fb, h * 64, 2 * a.sel_rows + r0);
+                    } else {
+                        tma_load_2d(smem_u32(V1(u)), &tm_kv, fb, 2 * a.D + h * 64, b * a.N + key0);
+                    }
                 }
             }
         }
+        PF(1);
+        if (lane == 0) PF_FLUSH(0);
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
@@ -354,11 +383,15 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             // PV products: A = [key][row] tiles (MN-major), B = V tiles (MN-major); the p . Vd product is subtracted
             const uint32_t idesc_o = umma_idesc_ex(128, 64, a.is_bf16, 1) | (1u << 15);
             const uint32_t idesc_neg = idesc_o | (1u << 13);  // a_negate
+            PF_DECL
             mbar_wait(smem_u32(q_full), 0);
+            PF(7);
             auto issue_s = [&](int t) {
                 const int u = t & 1;
-                mbar_wait(smem_u32(&kv_full[u]), (t >> 1) & 1);
+                mbar_wait(smem_u32(&k_full[u]), (t >> 1) & 1);
+                PF(0);
                 mbar_wait(smem_u32(&s_empty[u]), ((t >> 1) & 1) ^ 1);
+                PF(1);
                 tcgen05_fence_after();
                 for (int kb = 0; kb < nkb; ++kb) {
                     const uint64_t dq = umma_smem_desc(smem_u32(Qb(kb)));
@@ -369,18 +402,25 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                                         (kb > 0 || kk > 0));
                 }
                 tcgen05_commit(smem_u32(&s_full[u]));
+                tcgen05_commit(smem_u32(&k_empty[u]));
+                PF(2);
             };
             auto issue_pv = [&](int t) {
                 const int u = t & 1;
                 mbar_wait(smem_u32(p_ready), t & 1);
+                PF(3);
+                mbar_wait(smem_u32(&v_full[u]), (t >> 1) & 1);
+                PF(8);
                 tcgen05_fence_after();
                 const uint64_t dan = umma_smem_desc_mn_a(smem_u32(An));
                 const uint64_t dv1 = umma_smem_desc_mn(smem_u32(V1(u)));
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)  // 16 keys per step = 16 lines of 128 B (2048 B) in the A and V tiles
                     tcgen05_mma_f16(tmem_o, dan + (uint64_t)(128 * kk), dv1 + (uint64_t)(128 * kk), idesc_o, (t > 0 || kk > 0));
+                PF(4);
                 if (MODE == ET_ATTN_DELTA) {
                     mbar_wait(smem_u32(&ps_full[t % AP_PT_STAGES]), (t / AP_PT_STAGES) & 1);  // old state tile landed
+                    PF(5);
                     fence_proxy_async();  // cp.async (generic proxy) writes -> visible to the tensor core
                     const uint64_t dp = umma_smem_desc_mn_a(smem_u32(Pt(t % AP_PT_STAGES)));
                     const uint64_t dv2 = umma_smem_desc_mn(smem_u32(V2(u)));
@@ -390,17 +430,87 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 }
                 tcgen05_commit(smem_u32(&pv_done[u]));
                 if (t == T - 1) tcgen05_commit(smem_u32(o_full));
+                PF(6);
             };
             if (T > 0) issue_s(0);
             for (int t = 0; t < T; ++t) {
                 if (t + 1 < T) issue_s(t + 1);
                 issue_pv(t);
             }
+            PF_FLUSH(1);
+        }
+    } else if (warp < 4 || warp >= 12) {
+        // ------------------------------------------------------------------ A-gate state movers (4 warps, 128 threads)
+        // A selected column x this CTA's 128 rows is 256 contiguous bytes of the column-major state = 16 threads x 16 B;
+        // thread mt moves segment (mt & 15) of columns (mt >> 4) + 8 i, i < 8.  Per tile: prefetch the old state tile
+        // AP_PT_STAGES tiles ahead (cp.async straight into the MN-major A-operand layout) and write the new a_n tile back
+        // (modules.py:200).  Scattered 256-byte HBM segments stall the issuing warps (LSU back-pressure), so this traffic
+        // has its own warps and never holds up the exp / MMA pipeline.
+        if (MODE != ET_ATTN_DENSE) {
+            const int mt = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
+            const int segi = mt & 15, seg = segi * 8, col0 = mt >> 4;
+            auto tile_tok = [&](int tt, int i) -> int {  // token of column col0 + 8 i of tile tt (or -1)
+                const int j = tt * AP_KEYS + col0 + 8 * i;
+                if (j >= nkeys) return -1;
+                return (MODE == ET_ATTN_DELTA) ? (int)a.idx[(size_t)b * a.k + j] : j;
+            };
+            auto load_state = [&](int tt, const int (&tok)[8]) {  // a_state[:, idx of tile tt] -> Pt ring (A-operand layout)
+                uint8_t* dst = Pt(tt % AP_PT_STAGES);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint8_t* d = dst + a_chunk(col0 + 8 * i, segi);
+                    if (tok[i] >= 0) cp_async_16(smem_u32(d), a_state + a_head + (size_t)tok[i] * a.NP + q0 + seg);
+                    else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);  // ragged tile: p = 0, never garbage
+                }
+                cp_async_arrive_noinc(smem_u32(&ps_full[tt % AP_PT_STAGES]));
+            };
+            PF_DECL
+            int tok_next[8];
+            if (MODE == ET_ATTN_DELTA) {
+                for (int tt = 0; tt < AP_PT_STAGES && tt < T; ++tt) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) tok_next[i] = tile_tok(tt, i);
+                    load_state(tt, tok_next);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tok_next[i] = AP_PT_STAGES < T ? tile_tok(AP_PT_STAGES, i) : -1;
+            }
+            for (int t = 0; t < T; ++t) {
+                int tok_wb[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tok_wb[i] = tile_tok(t, i);
+                PF(0);
+                if (MODE == ET_ATTN_DELTA && t >= 1 && t - 1 + AP_PT_STAGES < T) {
+                    // ring slot of tile t-1 is free once its PV MMAs are done
+                    mbar_wait(smem_u32(&pv_done[(t - 1) & 1]), ((t - 1) >> 1) & 1);
+                    PF(1);
+                    load_state(t - 1 + AP_PT_STAGES, tok_next);
+                    if (t + AP_PT_STAGES < T) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) tok_next[i] = tile_tok(t + AP_PT_STAGES, i);
+                    }
+                    PF(2);
+                }
+                mbar_wait(smem_u32(p_ready), t & 1);  // every row of the a_n tile is written
+                PF(3);
+                uint4 wb[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) wb[i] = *reinterpret_cast<const uint4*>(An + a_chunk(col0 + 8 * i, segi));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(an_free));  // all chunks read: the a_n tile may be rewritten
+                PF(4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (tok_wb[i] >= 0)
+                        *reinterpret_cast<uint4*>(a_state + a_head + (size_t)tok_wb[i] * a.NP + q0 + seg) = wb[i];
+                PF(5);
+            }
+            if (warp == 2 && lane == 0) PF_FLUSH(3);
         }
     } else {
-        // ------------------------------------------------------------------ softmax / gate / epilogue
+        // ------------------------------------------------------------------ softmax / epilogue
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;  // key columns [32 half, +32) of every 64-key tile
+        const int half = (warp - 4) >> 2;  // key columns [32 half, +32) of every 64-key tile
         const int row = quarter * 32 + lane;
         const size_t grow = ((size_t)b * a.H + h) * a.N + q0 + row;
         const float m2 = a.stats[grow * 2];
@@ -409,49 +519,20 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // this thread's element (key, row) of an MN-major A tile: block row >> 6, line key, chunk (row >> 3) & 7
         const int a_row_off = (row >> 6) * 8192 + (row & 7) * 2;
         const int a_row_chunk = (row >> 3) & 7;
-        // A-gate state traffic is spread over the 256 softmax threads: a selected column x this CTA's 128 rows is 256
-        // contiguous bytes = 16 threads x 16 B; thread st moves segment (st & 15) of columns (st >> 4) + 16 i, i < 4.
-        const int st = threadIdx.x - 64;
-        const int seg = (st & 15) * 8, col0 = st >> 4;
-        auto tile_tok = [&](int tt, int i) -> int {  // token of column col0 + 16 i of tile tt (or -1)
-            const int j = tt * AP_KEYS + col0 + 16 * i;
-            if (j >= nkeys) return -1;
-            return (MODE == ET_ATTN_DELTA) ? (int)a.idx[(size_t)b * a.k + j] : j;
-        };
-        auto load_state = [&](int tt, const int (&tok)[4]) {  // a_state[:, idx of tile tt] -> Pt ring (A-operand layout)
-            uint8_t* dst = Pt(tt % AP_PT_STAGES);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint8_t* d = dst + a_chunk(col0 + 16 * i, st & 15);
-                if (tok[i] >= 0) cp_async_16(smem_u32(d), a_state + a_head + (size_t)tok[i] * a.NP + q0 + seg);
-                else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);  // ragged tile: p = 0, never garbage
-            }
-            cp_async_arrive_noinc(smem_u32(&ps_full[tt % AP_PT_STAGES]));
-        };
-        int tok_next[4] = {-1, -1, -1, -1};  // tokens of the tile AP_PT_STAGES ahead (index loads issued a tile early)
-        if (MODE == ET_ATTN_DELTA) {
-            for (int tt = 0; tt < AP_PT_STAGES && tt < T; ++tt) {
-                int tk0[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) tk0[i] = tile_tok(tt, i);
-                load_state(tt, tk0);
-            }
-            if (AP_PT_STAGES < T) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) tok_next[i] = tile_tok(AP_PT_STAGES, i);
-            }
-        }
+        PF_DECL
         for (int t = 0; t < T; ++t) {
             const int u = t & 1;
             const uint32_t ph = (t >> 1) & 1;
+            PF(11);
             mbar_wait(smem_u32(&s_full[u]), ph);
+            PF(0);
             tcgen05_fence_after();
             uint32_t v[32];
             tmem_load_32x32(taddr + (uint32_t)(u * AP_KEYS + half * 32), v);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_empty[u]));
-            const int* tk = s_tok + u * AP_KEYS + half * 32;
+            PF(1);
             const bool full_tile = (t + 1) * AP_KEYS <= nkeys;
             // normalised attention values of the selected columns, rounded to dtype exactly as stored in the state
             uint32_t an[16];  // element pairs: key 2i in the low half of word i
@@ -464,11 +545,18 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (!full_tile) {  // ragged last tile: keys beyond k contribute nothing
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    if (tk[2 * i] < 0) an[i] &= 0xffff0000u;
-                    if (tk[2 * i + 1] < 0) an[i] &= 0x0000ffffu;
+                    const int j = t * AP_KEYS + half * 32 + 2 * i;
+                    if (j >= nkeys) an[i] &= 0xffff0000u;
+                    if (j + 1 >= nkeys) an[i] &= 0x0000ffffu;
                 }
             }
-            if (t >= 1) mbar_wait(smem_u32(&pv_done[(t - 1) & 1]), ((t - 1) >> 1) & 1);  // a_n tile of t-1 consumed
+            PF(2);
+            if (t >= 1) {
+                // the a_n tile of t-1 has been consumed by the PV MMAs and copied out by the write-back warps
+                mbar_wait(smem_u32(&pv_done[(t - 1) & 1]), ((t - 1) >> 1) & 1);
+                if (MODE != ET_ATTN_DENSE) mbar_wait(smem_u32(an_free), (t - 1) & 1);
+            }
+            PF(3);
             {
                 uint8_t* dst = An + a_row_off;
 #pragma unroll
@@ -478,34 +566,13 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     *reinterpret_cast<uint16_t*>(dst + k1 * 128 + ((a_row_chunk ^ (k1 & 7)) << 4)) = (uint16_t)(an[i] >> 16);
                 }
             }
+            PF(4);
             fence_proxy_async();  // generic-proxy smem writes -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(p_ready));
-            if (MODE != ET_ATTN_DENSE) {
-                // write the updated columns back: a_state[:, idx] = a_n (modules.py:200)
-                asm volatile("bar.sync 1, 256;" ::: "memory");  // every row of the a_n tile is written
-                uint4 wb[4];
-                int tk_wb[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    tk_wb[i] = s_tok[u * AP_KEYS + col0 + 16 * i];
-                    wb[i] = *reinterpret_cast<const uint4*>(An + a_chunk(col0 + 16 * i, st & 15));
-                }
-                asm volatile("bar.sync 2, 256;" ::: "memory");  // all chunks read: the a_n tile may be rewritten
-                // refill the p ring: the slot of tile t - 1 is free once its PV MMAs are done (pv_done(t-1), waited above)
-                if (MODE == ET_ATTN_DELTA && t >= 1 && t - 1 + AP_PT_STAGES < T) {
-                    load_state(t - 1 + AP_PT_STAGES, tok_next);
-                    if (t + AP_PT_STAGES < T) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) tok_next[i] = tile_tok(t + AP_PT_STAGES, i);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (tk_wb[i] >= 0)
-                        *reinterpret_cast<uint4*>(a_state + a_head + (size_t)tk_wb[i] * a.NP + q0 + seg) = wb[i];
-            }
+            PF(5);
         }
+        PF(11);
         // ---- epilogue: acc += O, out = acc ; each thread writes its row's 32 of the head's 64 output columns
         uint16_t* acc = static_cast<uint16_t*>(a.acc);
         uint16_t* out = static_cast<uint16_t*>(a.out);
@@ -538,6 +605,8 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (MODE != ET_ATTN_DENSE) *reinterpret_cast<uint4*>(acc + off + c * 8) = pk;
             *reinterpret_cast<uint4*>(out + off + c * 8) = pk;
         }
+        PF(12);
+        if (lane == 0 && warp == 4) PF_FLUSH(2);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -609,11 +678,11 @@ int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, i
     }
     if (mode == ET_ATTN_DELTA) {
         if ((rc = make_tmap_2d(&tmsel, sel, 3LL * a.sel_rows, (long long)a.D, 64, a.is_bf16))) return rc;
-        et_launch(tc_apply_kernel<BF16, ET_ATTN_DELTA>, dim3(grid), dim3(kThreads), AP_SMEM, s, tm128, tmsel, tmbh, tmbw, tmoh, a);
+        et_launch(tc_apply_kernel<BF16, ET_ATTN_DELTA>, dim3(grid), dim3(kApThreads), AP_SMEM, s, tm128, tmsel, tmbh, tmbw, tmoh, a);
     } else if (mode == ET_ATTN_FIRST) {
-        et_launch(tc_apply_kernel<BF16, ET_ATTN_FIRST>, dim3(grid), dim3(kThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
+        et_launch(tc_apply_kernel<BF16, ET_ATTN_FIRST>, dim3(grid), dim3(kApThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
     } else {
-        et_launch(tc_apply_kernel<BF16, ET_ATTN_DENSE>, dim3(grid), dim3(kThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
+        et_launch(tc_apply_kernel<BF16, ET_ATTN_DENSE>, dim3(grid), dim3(kApThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
     }
     ET_COUNT_LAUNCH(1);
     if (g_tc_time_apply) cudaEventRecord(g_ev1, s);
@@ -640,5 +709,6 @@ int et_tc_global_attention(const void* qkv, const void* sel, void* onehot, const
     a.sel_rows = B * k;
     a.has_bias = bias_h != nullptr;
     a.c1 = 0.125f * kLog2e;
+    a.prof = g_tc_prof;
     return is_bf16 ? launch_tc<true>(qkv, sel, onehot, a, mode, stream) : launch_tc<false>(qkv, sel, onehot, a, mode, stream);
 }

@@ -210,6 +210,7 @@ int g_force_depth = 0;  // test / tuning hook: et_debug_set(5, 1 = deep pipeline
 extern int g_attn_tc;
 extern unsigned long long* g_gate_dbg;
 extern int g_tc_time_apply;
+extern unsigned long long* g_tc_prof;
 
 extern "C" {
 
@@ -228,6 +229,10 @@ int et_debug_set(int key, long long value) {
     }
     if (key == 2) {
         g_attn_tc = value != 0;
+        return ET_OK;
+    }
+    if (key == 4) {
+        g_tc_prof = reinterpret_cast<unsigned long long*>(value);
         return ET_OK;
     }
     if (key == 3) {
