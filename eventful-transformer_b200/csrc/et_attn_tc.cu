@@ -79,6 +79,14 @@ __device__ __forceinline__ uint32_t float_to_elem(float v) {
     else return (uint32_t)__half_as_ushort(__float2half_rn(v));
 }
 
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2_elem(float lo, float hi) {  // one F2FP; `lo` in bits 0-15
+    uint32_t r;
+    if constexpr (BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 __device__ __forceinline__ void named_sync_softmax() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ============================================================================================= phase A
@@ -519,6 +527,14 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // this thread's element (key, row) of an MN-major A tile: block row >> 6, line key, chunk (row >> 3) & 7
         const int a_row_off = (row >> 6) * 8192 + (row & 7) * 2;
         const int a_row_chunk = (row >> 3) & 7;
+        // previous accumulator values of this thread's output slice: loaded now, consumed in the epilogue
+        uint16_t* acc = static_cast<uint16_t*>(a.acc);
+        uint16_t* out = static_cast<uint16_t*>(a.out);
+        const size_t off = ((size_t)b * a.N + q0 + row) * a.D + h * 64 + half * 32;
+        uint4 prev[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            prev[c] = (MODE == ET_ATTN_DELTA) ? *reinterpret_cast<const uint4*>(acc + off + c * 8) : make_uint4(0, 0, 0, 0);
         PF_DECL
         for (int t = 0; t < T; ++t) {
             const int u = t & 1;
@@ -540,7 +556,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int i = 0; i < 16; ++i) {
                 const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), a.c1, -m2)) * linv;
                 const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), a.c1, -m2)) * linv;
-                an[i] = float_to_elem<BF16>(p0) | (float_to_elem<BF16>(p1) << 16);
+                an[i] = pack2_elem<BF16>(p0, p1);
             }
             if (!full_tile) {  // ragged last tile: keys beyond k contribute nothing
 #pragma unroll
@@ -574,24 +590,21 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         PF(11);
         // ---- epilogue: acc += O, out = acc ; each thread writes its row's 32 of the head's 64 output columns
-        uint16_t* acc = static_cast<uint16_t*>(a.acc);
-        uint16_t* out = static_cast<uint16_t*>(a.out);
-        const size_t off = ((size_t)b * a.N + q0 + row) * a.D + h * 64 + half * 32;
         uint32_t o[32];
         if (T > 0) {
             mbar_wait(smem_u32(o_full), 0);
+            PF(12);
             tcgen05_fence_after();
             tmem_load_32x32(taddr + (uint32_t)(2 * AP_KEYS + half * 32), o);
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = 0u;
         }
+        PF(13);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             uint32_t w[4];
-            uint4 prev = make_uint4(0, 0, 0, 0);
-            if (MODE == ET_ATTN_DELTA) prev = *reinterpret_cast<const uint4*>(acc + off + c * 8);
-            const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
+            const uint32_t pw[4] = {prev[c].x, prev[c].y, prev[c].z, prev[c].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float lo = __uint_as_float(o[c * 8 + 2 * i]), hi = __uint_as_float(o[c * 8 + 2 * i + 1]);
@@ -599,13 +612,13 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     lo += elem_to_float<BF16>((uint16_t)(pw[i] & 0xffffu));
                     hi += elem_to_float<BF16>((uint16_t)(pw[i] >> 16));
                 }
-                w[i] = float_to_elem<BF16>(lo) | (float_to_elem<BF16>(hi) << 16);
+                w[i] = pack2_elem<BF16>(lo, hi);
             }
             const uint4 pk = make_uint4(w[0], w[1], w[2], w[3]);
             if (MODE != ET_ATTN_DENSE) *reinterpret_cast<uint4*>(acc + off + c * 8) = pk;
             *reinterpret_cast<uint4*>(out + off + c * 8) = pk;
         }
-        PF(12);
+        PF(14);
         if (lane == 0 && warp == 4) PF_FLUSH(2);
     }
     tcgen05_fence_before();

@@ -38,6 +38,13 @@ struct WinArgs {
 };
 
 template <bool BF16>
+__device__ __forceinline__ uint32_t pack2_elem(float lo, float hi) {  // one F2FP; `lo` in bits 0-15
+    uint32_t r;
+    if constexpr (BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <bool BF16>
 __device__ __forceinline__ uint32_t to_elem(float v) {
     if constexpr (BF16) return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
     else return (uint32_t)__half_as_ushort(__float2half_rn(v));
@@ -205,25 +212,31 @@ tc_window_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         uint8_t* pt = smem + m * 2 * W_PBLK + (row >> 6) * W_PBLK + (row & 7) * 2;
         const int rchunk = (row >> 3) & 7;
         float sum = 0.f;
-        auto emit = [&](int key, float x) {
-            float p = 0.f;
+        auto emit2 = [&](int key, float x0, float x1) {  // keys key, key + 1 (key even)
+            float p0 = 0.f, p1 = 0.f;
             if (key < a.Wn) {
-                p = ex2_approx(fmaf(x, a.c1, -m2));
-                sum += p;
+                p0 = ex2_approx(fmaf(x0, a.c1, -m2));
+                sum += p0;
             }
-            *reinterpret_cast<uint16_t*>(pt + key * 128 + ((rchunk ^ (key & 7)) << 4)) = (uint16_t)to_elem<BF16>(p);
+            if (key + 1 < a.Wn) {
+                p1 = ex2_approx(fmaf(x1, a.c1, -m2));
+                sum += p1;
+            }
+            const uint32_t pk = pack2_elem<BF16>(p0, p1);
+            *reinterpret_cast<uint16_t*>(pt + key * 128 + ((rchunk ^ (key & 7)) << 4)) = (uint16_t)(pk & 0xffffu);
+            *reinterpret_cast<uint16_t*>(pt + (key + 1) * 128 + ((rchunk ^ ((key + 1) & 7)) << 4)) = (uint16_t)(pk >> 16);
         };
         for (int c0 = 0; c0 < a.NK; c0 += 32) {
             if (c0 + 32 <= a.NK) {
                 uint32_t v[32];
                 tmem_load_32x32(taddr + (uint32_t)c0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) emit(c0 + i, __uint_as_float(v[i]));
+                for (int i = 0; i < 32; i += 2) emit2(c0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
             } else {
                 uint32_t v[16];
                 tmem_load_32x16(taddr + (uint32_t)c0, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) emit(c0 + i, __uint_as_float(v[i]));
+                for (int i = 0; i < 16; i += 2) emit2(c0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
             }
         }
         tcgen05_fence_before();
@@ -249,7 +262,7 @@ tc_window_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int e = (c & 3) * 8 + 2 * i;
-                    w[i] = to_elem<BF16>(__uint_as_float(src[e]) * inv) | (to_elem<BF16>(__uint_as_float(src[e + 1]) * inv) << 16);
+                    w[i] = pack2_elem<BF16>(__uint_as_float(src[e]) * inv, __uint_as_float(src[e + 1]) * inv);
                 }
                 *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
             }

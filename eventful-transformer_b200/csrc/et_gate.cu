@@ -72,7 +72,11 @@ __device__ __forceinline__ void load_row(const T* xa, const T* xb, T* xsum, size
                 uint4 ub = ld_stream16(xb + off + (size_t)ch * VEC);
                 unpack16<T>(ub, w);
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) v[c * VEC + i] = round_to<T>(v[c * VEC + i] + w[i]);
+                for (int i = 0; i < VEC; i += 2) {
+                    v[c * VEC + i] += w[i];
+                    v[c * VEC + i + 1] += w[i + 1];
+                    round2_to<T>(v[c * VEC + i], v[c * VEC + i + 1]);
+                }
                 if (xsum != nullptr) st16(xsum + off + (size_t)ch * VEC, pack16<T>(&v[c * VEC]));
             }
         } else {
@@ -112,8 +116,11 @@ __device__ __forceinline__ void layer_norm_row(float (&v)[CPL * ElemTraits<T>::V
             unpack16<T>(ld16(w + (size_t)ch * VEC), g);
             unpack16<T>(ld16(b + (size_t)ch * VEC), o);
 #pragma unroll
-            for (int i = 0; i < VEC; ++i)
-                v[c * VEC + i] = round_to<T>((v[c * VEC + i] - mean) * rstd * g[i] + o[i]);
+            for (int i = 0; i < VEC; i += 2) {
+                v[c * VEC + i] = (v[c * VEC + i] - mean) * rstd * g[i] + o[i];
+                v[c * VEC + i + 1] = (v[c * VEC + i + 1] - mean) * rstd * g[i + 1] + o[i + 1];
+                round2_to<T>(v[c * VEC + i], v[c * VEC + i + 1]);
+            }
         }
     }
 }
@@ -333,7 +340,11 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
                 float w[VEC];
                 unpack16<T>(rw.xb[c], w);
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) v[c * VEC + i] = round_to<T>(v[c * VEC + i] + w[i]);
+                for (int i = 0; i < VEC; i += 2) {
+                    v[c * VEC + i] += w[i];
+                    v[c * VEC + i + 1] += w[i + 1];
+                    round2_to<T>(v[c * VEC + i], v[c * VEC + i + 1]);
+                }
                 if (xsum != nullptr && valid && ch < nchunks) st16(xsum + off + (size_t)ch * VEC, pack16<T>(&v[c * VEC]));
             }
         }
@@ -345,9 +356,15 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
                 float q[VEC];
                 if (p != nullptr) unpack16<T>(rw.p[c], q);
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const float e = (p != nullptr) ? round_to<T>(v[c * VEC + i] - q[i]) : v[c * VEC + i];
-                    ss = fmaf(e, e, ss);
+                for (int i = 0; i < VEC; i += 2) {
+                    float e0 = v[c * VEC + i], e1 = v[c * VEC + i + 1];
+                    if (p != nullptr) {
+                        e0 -= q[i];
+                        e1 -= q[i + 1];
+                        round2_to<T>(e0, e1);
+                    }
+                    ss = fmaf(e0, e0, ss);
+                    ss = fmaf(e1, e1, ss);
                 }
             }
         }

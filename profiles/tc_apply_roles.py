@@ -23,7 +23,8 @@ ROLES = {
                                  4: "read a_n chunks + release", 5: "state stores (STG.128)"}),
 }
 SM = {0: "wait s_full", 1: "tcgen05.ld + release S", 2: "exp2 / round", 3: "wait pv_done + an_free (t-1)", 4: "a_n tile stores",
-      5: "fence.proxy + arrive p_ready", 11: "loop overhead", 12: "epilogue"}
+      5: "fence.proxy + arrive p_ready", 11: "loop overhead", 12: "epilogue: wait o_full", 13: "epilogue: tcgen05.ld",
+      14: "epilogue: add + stores"}
 for order in ("ascending (what top-k emits)", "random"):
     idx = torch.randperm(n, device=dev)[:k]
     if order.startswith("asc"): idx = idx.sort().values
