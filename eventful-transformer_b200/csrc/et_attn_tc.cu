@@ -26,7 +26,7 @@
 //                    FIRST / DENSE modes run the same pipeline over all keys with V from the QKV buffer.
 // Warp roles.  tc_stats (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator and single-thread MMA issuer,
 // warps 2-9 = softmax: two warps per TMEM lane quarter, each thread owns one query row and half of the tile's key
-// columns.  tc_apply (448 threads): the same plus four state-mover warps (2, 3, 12, 13) that own all A-gate state
+// columns.  tc_apply (576 threads): the same plus eight state-mover warps (2, 3, 12-17) that own all A-gate state
 // traffic; its softmax / epilogue warps are 4-11.
 #include "et_tcgen05.cuh"
 
@@ -255,7 +255,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
 }
 
 // ============================================================================================= phase B
-constexpr int kApThreads = 448;  // warp 0 TMA, 1 MMA, 2-3 + 12-13 state movers, 4-11 softmax
+constexpr int kMoverWarps = 8;                        // warps 2-3 and 12 .. 12 + kMoverWarps - 3
+constexpr int kApThreads = (10 + kMoverWarps) * 32;  // warp 0 TMA, 1 MMA, 4-11 softmax, the rest state movers
+constexpr int MV_CPT = 1024 / (kMoverWarps * 32);    // 16-byte chunks per mover thread and tile
+constexpr int MV_CSTEP = kMoverWarps * 2;            // columns covered by one pass of the mover threads
 constexpr int AP_KEYS = 64;
 constexpr int AP_BLK = AP_KEYS * 64 * 2;          // 8 KB: one 64-key x 64-column operand block
 constexpr int AP_STAGE = 5 * AP_BLK;              // K, onehot-y, onehot-x, V1, V2
@@ -313,7 +316,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_init(smem_u32(q_full), 1);
         mbar_init(smem_u32(o_full), 1);
         mbar_init(smem_u32(p_ready), 8);
-        mbar_init(smem_u32(an_free), 4);
+        mbar_init(smem_u32(an_free), kMoverWarps);
         for (int u = 0; u < 2; ++u) {
             mbar_init(smem_u32(&k_full[u]), 1);
             mbar_init(smem_u32(&v_full[u]), 1);
@@ -322,7 +325,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_init(smem_u32(&s_empty[u]), 8);
             mbar_init(smem_u32(&pv_done[u]), 1);
         }
-        for (int u = 0; u < AP_PT_STAGES; ++u) mbar_init(smem_u32(&ps_full[u]), 128);
+        for (int u = 0; u < AP_PT_STAGES; ++u) mbar_init(smem_u32(&ps_full[u]), kMoverWarps * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
@@ -448,9 +451,9 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             PF_FLUSH(1);
         }
     } else if (warp < 4 || warp >= 12) {
-        // ------------------------------------------------------------------ A-gate state movers (4 warps, 128 threads)
+        // ------------------------------------------------------------------ A-gate state movers
         // A selected column x this CTA's 128 rows is 256 contiguous bytes of the column-major state = 16 threads x 16 B;
-        // thread mt moves segment (mt & 15) of columns (mt >> 4) + 8 i, i < 8.  Per tile: prefetch the old state tile
+        // thread mt moves segment (mt & 15) of columns (mt >> 4) + MV_CSTEP i, i < MV_CPT.  Per tile: prefetch the old state tile
         // AP_PT_STAGES tiles ahead (cp.async straight into the MN-major A-operand layout) and write the new a_n tile back
         // (modules.py:200).  Scattered 256-byte HBM segments stall the issuing warps (LSU back-pressure), so this traffic
         // has its own warps and never holds up the exp / MMA pipeline.
@@ -458,35 +461,35 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const int mt = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
             const int segi = mt & 15, seg = segi * 8, col0 = mt >> 4;
             auto tile_tok = [&](int tt, int i) -> int {  // token of column col0 + 8 i of tile tt (or -1)
-                const int j = tt * AP_KEYS + col0 + 8 * i;
+                const int j = tt * AP_KEYS + col0 + MV_CSTEP * i;
                 if (j >= nkeys) return -1;
                 return (MODE == ET_ATTN_DELTA) ? (int)a.idx[(size_t)b * a.k + j] : j;
             };
-            auto load_state = [&](int tt, const int (&tok)[8]) {  // a_state[:, idx of tile tt] -> Pt ring (A-operand layout)
+            auto load_state = [&](int tt, const int (&tok)[MV_CPT]) {  // a_state[:, idx of tile tt] -> Pt ring (A-operand layout)
                 uint8_t* dst = Pt(tt % AP_PT_STAGES);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    uint8_t* d = dst + a_chunk(col0 + 8 * i, segi);
+                for (int i = 0; i < MV_CPT; ++i) {
+                    uint8_t* d = dst + a_chunk(col0 + MV_CSTEP * i, segi);
                     if (tok[i] >= 0) cp_async_16(smem_u32(d), a_state + a_head + (size_t)tok[i] * a.NP + q0 + seg);
                     else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);  // ragged tile: p = 0, never garbage
                 }
                 cp_async_arrive_noinc(smem_u32(&ps_full[tt % AP_PT_STAGES]));
             };
             PF_DECL
-            int tok_next[8];
+            int tok_next[MV_CPT];
             if (MODE == ET_ATTN_DELTA) {
                 for (int tt = 0; tt < AP_PT_STAGES && tt < T; ++tt) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) tok_next[i] = tile_tok(tt, i);
+                    for (int i = 0; i < MV_CPT; ++i) tok_next[i] = tile_tok(tt, i);
                     load_state(tt, tok_next);
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) tok_next[i] = AP_PT_STAGES < T ? tile_tok(AP_PT_STAGES, i) : -1;
+                for (int i = 0; i < MV_CPT; ++i) tok_next[i] = AP_PT_STAGES < T ? tile_tok(AP_PT_STAGES, i) : -1;
             }
             for (int t = 0; t < T; ++t) {
-                int tok_wb[8];
+                int tok_wb[MV_CPT];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) tok_wb[i] = tile_tok(t, i);
+                for (int i = 0; i < MV_CPT; ++i) tok_wb[i] = tile_tok(t, i);
                 PF(0);
                 if (MODE == ET_ATTN_DELTA && t >= 1 && t - 1 + AP_PT_STAGES < T) {
                     // ring slot of tile t-1 is free once its PV MMAs are done
@@ -495,22 +498,23 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     load_state(t - 1 + AP_PT_STAGES, tok_next);
                     if (t + AP_PT_STAGES < T) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) tok_next[i] = tile_tok(t + AP_PT_STAGES, i);
+                        for (int i = 0; i < MV_CPT; ++i) tok_next[i] = tile_tok(t + AP_PT_STAGES, i);
                     }
                     PF(2);
                 }
                 mbar_wait(smem_u32(p_ready), t & 1);  // every row of the a_n tile is written
                 PF(3);
-                uint4 wb[8];
+                uint4 wb[MV_CPT];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) wb[i] = *reinterpret_cast<const uint4*>(An + a_chunk(col0 + 8 * i, segi));
+                for (int i = 0; i < MV_CPT; ++i) wb[i] = *reinterpret_cast<const uint4*>(An + a_chunk(col0 + MV_CSTEP * i, segi));
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(an_free));  // all chunks read: the a_n tile may be rewritten
                 PF(4);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (tok_wb[i] >= 0)
-                        *reinterpret_cast<uint4*>(a_state + a_head + (size_t)tok_wb[i] * a.NP + q0 + seg) = wb[i];
+                for (int i = 0; i < MV_CPT; ++i)
+                    if (tok_wb[i] >= 0)  // evict-first: the 400 MB of state columns stream through L2 once per frame
+                        asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a_state + a_head + (size_t)tok_wb[i] * a.NP + q0 + seg),
+                                     "r"(wb[i].x), "r"(wb[i].y), "r"(wb[i].z), "r"(wb[i].w) : "memory");
                 PF(5);
             }
             if (warp == 2 && lane == 0) PF_FLUSH(3);
@@ -521,12 +525,22 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int half = (warp - 4) >> 2;  // key columns [32 half, +32) of every 64-key tile
         const int row = quarter * 32 + lane;
         const size_t grow = ((size_t)b * a.H + h) * a.N + q0 + row;
-        const float m2 = a.stats[grow * 2];
-        const float linv = 1.f / a.stats[grow * 2 + 1];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        // this thread's element (key, row) of an MN-major A tile: block row >> 6, line key, chunk (row >> 3) & 7
-        const int a_row_off = (row >> 6) * 8192 + (row & 7) * 2;
-        const int a_row_chunk = (row >> 3) & 7;
+        // The S' tile is read in mma-fragment shape (tcgen05.ld 16x256b): this thread owns, for a < 4, query row
+        // quarter * 32 + 8 a + lane / 4 and key columns 8 n + 2 (lane % 4), + 1 (n < 4) of its 32-key half.  After
+        // exp / normalise / pack the registers are 8x8 b16 fragments, and stmatrix.trans writes each as eight 16-byte
+        // chunks (one key x 8 rows): exactly the MN-major, 128B-swizzled A-operand tile, 4 stores per thread and tile.
+        const int lr = lane >> 2, lc = (lane & 3) * 2;
+        float m2r[4], linvr[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t g = ((size_t)b * a.H + h) * a.N + q0 + quarter * 32 + 8 * i + lr;
+            m2r[i] = a.stats[g * 2];
+            linvr[i] = 1.f / a.stats[g * 2 + 1];
+        }
+        // stmatrix: lane 8 g + j addresses key (32 half + 8 n + j), rows quarter * 32 + 8 g ... + 7
+        const int sm_r = quarter * 32 + 8 * (lane >> 3), sm_j = lane & 7;
+        const uint32_t st_addr0 = smem_u32(An) + (sm_r >> 6) * 8192 + (half * 32 + sm_j) * 128 + ((((sm_r >> 3) & 7) ^ sm_j) << 4);
         // previous accumulator values of this thread's output slice: loaded now, consumed in the epilogue
         uint16_t* acc = static_cast<uint16_t*>(a.acc);
         uint16_t* out = static_cast<uint16_t*>(a.out);
@@ -543,27 +557,35 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(smem_u32(&s_full[u]), ph);
             PF(0);
             tcgen05_fence_after();
-            uint32_t v[32];
-            tmem_load_32x32(taddr + (uint32_t)(u * AP_KEYS + half * 32), v);
+            uint32_t v0[16], v1[16];  // lanes 0-15 / 16-31 of this warp's TMEM quarter
+            tmem_load_16x256b_x4(taddr + (uint32_t)(u * AP_KEYS + half * 32), v0);
+            tmem_load_16x256b_x4(taddr + (16u << 16) + (uint32_t)(u * AP_KEYS + half * 32), v1);
+            tmem_wait_ld();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_empty[u]));
             PF(1);
             const bool full_tile = (t + 1) * AP_KEYS <= nkeys;
             // normalised attention values of the selected columns, rounded to dtype exactly as stored in the state
-            uint32_t an[16];  // element pairs: key 2i in the low half of word i
+            uint32_t fr[4][4];  // [key group n][row block i]: keys 8 n + lc (low half), + 1 (high half)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), a.c1, -m2)) * linv;
-                const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), a.c1, -m2)) * linv;
-                an[i] = pack2_elem<BF16>(p0, p1);
+            for (int n = 0; n < 4; ++n) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t* src = i < 2 ? v0 : v1;
+                    const int e = 4 * n + 2 * (i & 1);
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(src[e]), a.c1, -m2r[i])) * linvr[i];
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(src[e + 1]), a.c1, -m2r[i])) * linvr[i];
+                    fr[n][i] = pack2_elem<BF16>(p0, p1);
+                }
             }
             if (!full_tile) {  // ragged last tile: keys beyond k contribute nothing
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int j = t * AP_KEYS + half * 32 + 2 * i;
-                    if (j >= nkeys) an[i] &= 0xffff0000u;
-                    if (j + 1 >= nkeys) an[i] &= 0x0000ffffu;
+                for (int n = 0; n < 4; ++n) {
+                    const int j = t * AP_KEYS + half * 32 + 8 * n + lc;
+                    const uint32_t mask = (j >= nkeys ? 0u : 0x0000ffffu) | (j + 1 >= nkeys ? 0u : 0xffff0000u);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) fr[n][i] &= mask;
                 }
             }
             PF(2);
@@ -573,15 +595,8 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 if (MODE != ET_ATTN_DENSE) mbar_wait(smem_u32(an_free), (t - 1) & 1);
             }
             PF(3);
-            {
-                uint8_t* dst = An + a_row_off;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int k0 = half * 32 + 2 * i, k1 = k0 + 1;
-                    *reinterpret_cast<uint16_t*>(dst + k0 * 128 + ((a_row_chunk ^ (k0 & 7)) << 4)) = (uint16_t)(an[i] & 0xffffu);
-                    *reinterpret_cast<uint16_t*>(dst + k1 * 128 + ((a_row_chunk ^ (k1 & 7)) << 4)) = (uint16_t)(an[i] >> 16);
-                }
-            }
+            for (int n = 0; n < 4; ++n) stmatrix_x4_trans(st_addr0 + n * 1024, fr[n][0], fr[n][1], fr[n][2], fr[n][3]);
             PF(4);
             fence_proxy_async();  // generic-proxy smem writes -> visible to tcgen05.mma
             __syncwarp();

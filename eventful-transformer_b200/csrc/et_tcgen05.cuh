@@ -70,6 +70,27 @@ __device__ __forceinline__ void tmem_load_32x32(uint32_t taddr, uint32_t (&r)[32
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 lanes x (4 x 256 bit): the mma-fragment-shaped TMEM load.  Thread t receives, for column group n < 4,
+// r[4n], r[4n+1] = lane (t / 4), 32-bit columns 8n + 2 (t % 4), + 1 and r[4n+2], r[4n+3] = the same columns of lane
+// (t / 4) + 8.  `taddr` lane = 32 (warp % 4) or that + 16.  No wait inside: pair with tmem_wait_ld().
+__device__ __forceinline__ void tmem_load_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Four 8x8 b16 matrices, stored transposed: lane 8 g + j supplies the address of the 16-byte row j of matrix g; a
+// thread's register i holds (row t / 4, columns 2 (t % 4), + 1) of matrix i, which lands in memory rows 2 (t % 4), + 1
+// at position t / 4 -- registers in mma-fragment layout become column-contiguous (MN-major) operand chunks.
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2),
+                 "r"(r3) : "memory");
+}
+
 // K-major operand tile with 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
