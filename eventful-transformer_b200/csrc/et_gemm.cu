@@ -5,8 +5,10 @@
 // Warp-specialised, one 128 x BLOCK_N output tile per CTA:
 //   warp 0    : TMA producer   (cp.async.bulk.tensor 2-D, 128-byte swizzle, K slices of 64)
 //   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, fp32 accumulate in TMEM)
-//   warps 2-5 : epilogue       (tcgen05.ld 32 lanes x 32 columns -> bias / GELU -> 16-byte row stores,
-//                               rows redirected through the gate's index = TokenBuffer scatter)
+//   warps 2-9 : epilogue       two warps per TMEM lane quarter, half of the tile's columns each:
+//                               tcgen05.ld -> bias / GELU -> packed 16-byte chunks into a swizzled staging tile (the
+//                               dead smem ring), then row-contiguous 16-byte stores (a warp writes whole output rows),
+//                               rows redirected through the gate's index = TokenBuffer scatter
 // smem ring of STAGES {A 128x64, W BLOCK_Nx64} tiles guarded by full/empty mbarriers; the MMA warp
 // releases a stage with tcgen05.commit and signals the epilogue through a third barrier.
 // TMA out-of-bounds zero fill handles the M / n_feat / K tails, so any M, K % 8 == 0 and
@@ -18,7 +20,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 16-bit = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 struct LinearArgs {
@@ -28,18 +30,48 @@ struct LinearArgs {
     const int* count;
     long long ld_out;
     int M, K, n_feat, act, k, n_out_rows, is_bf16;
+    unsigned long long* prof;
 };
 
 using namespace et_tc;
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// et_debug_set(7, device pointer to 3 x 16 u64): per-role cycle buckets of linear_tcgen05_kernel, summed over CTAs
+// (profiling build only: make prof).
+unsigned long long* g_gemm_prof = nullptr;
+#ifdef ET_TC_PROFILE
+#define GPF_DECL long long pf_[16]; for (int i_ = 0; i_ < 16; ++i_) pf_[i_] = 0; long long pf_t_ = clock64();
+#define GPF(i) do { const long long n_ = clock64(); pf_[i] += n_ - pf_t_; pf_t_ = n_; } while (0)
+#define GPF_FLUSH(role) do { if (args.prof) for (int i_ = 0; i_ < 16; ++i_) atomicAdd(args.prof + (role) * 16 + i_, (unsigned long long)pf_[i_]); } while (0)
+#else
+#define GPF_DECL
+#define GPF(i)
+#define GPF_FLUSH(role)
+#endif
+
+// GELU(x) = x Phi(x) with the exact-erf definition (torch.nn.GELU default).  erfc by Abramowitz-Stegun 7.1.26
+// (|error| < 1.5e-7, far below the 16-bit output rounding) on the FMA pipe plus two MUFU ops; libdevice's erff costs
+// ~40 instructions per element and made the mlp_1 epilogue longer than its mainloop.  Both tails are cancellation-free:
+// x Phi(x) = x (1 - q / 2) for x >= 0 and x q / 2 for x < 0, with q = erfc(|x| / sqrt 2).
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float q = poly * t * ex2_approx(-1.4426950408889634f * z * z);
+    return x * (x >= 0.f ? fmaf(-0.5f, q, 1.f) : 0.5f * q);
+}
 
 template <int BLOCK_N, int STAGES>
 struct GemmSmem {
     static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+    static constexpr int ROW_OFFSET = BAR_OFFSET + 256;     // int[128]: scatter target row of every tile row
+    static constexpr int TOTAL = ROW_OFFSET + 512 + 1024;   // barriers + row table + alignment slack
+    static constexpr int OUT_STRIDE = (BLOCK_N * 2 + 127) / 128 * 128;  // staging tile row pitch (whole swizzle groups)
+    static_assert(BLOCK_M * OUT_STRIDE <= STAGES * STAGE_BYTES, "epilogue staging tile must fit in the smem ring");
 };
 
 template <int BLOCK_N, int STAGES>
@@ -57,6 +89,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint64_t* tmem_full_bar = bars + 2 * STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
+    GPF_DECL
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BLOCK_N;
@@ -83,19 +116,24 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    GPF(0);  // prologue: barrier init, TMEM allocation, CTA sync
 
     if (warp == 0) {
         if (lane == 0) {
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t parity = (kb / STAGES) & 1;
+                GPF(2);
                 mbar_wait(smem_u32(&empty_bar[s]), parity ^ 1);
+                GPF(1);
                 const uint32_t a_dst = smem_u32(smem + s * L::STAGE_BYTES);
                 const uint32_t fb = smem_u32(&full_bar[s]);
                 mbar_expect_tx(fb, L::STAGE_BYTES);
                 tma_load_2d(a_dst, &tmap_a, fb, kb * BLOCK_K, m0);
                 tma_load_2d(a_dst + A_TILE_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
             }
+            GPF(2);
+            GPF_FLUSH(0);
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -103,7 +141,9 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t parity = (kb / STAGES) & 1;
+                GPF(2);
                 mbar_wait(smem_u32(&full_bar[s]), parity);
+                if (kb == 0) GPF(3); else GPF(1);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
                 const uint64_t da = umma_smem_desc(a_addr);
@@ -117,58 +157,100 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 tcgen05_commit(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs retire
             }
             tcgen05_commit(smem_u32(tmem_full_bar));  // accumulator complete
+            GPF(2);
+            GPF_FLUSH(1);
         }
     } else {
         // ---- epilogue: warp w may only touch TMEM lanes [32 * (w % 4), +32)
+        const int ew = warp - 2;
         const int quarter = warp & 3;
+        const int chalf = ew >> 2;  // which half of the tile's columns this warp converts
         const int row = quarter * 32 + lane;
         const int m = m0 + row;
-        bool valid = m < args.M;
-        long long out_row = m;
-        if (valid && args.idx != nullptr) {
-            const int b = m / args.k, j = m - b * args.k;
-            if (args.count != nullptr && j >= args.count[b]) valid = false;
-            if (valid) out_row = (long long)b * args.n_out_rows + args.idx[m];
+        int* s_row = reinterpret_cast<int*>(smem + L::ROW_OFFSET);
+        if (chalf == 0) {
+            bool valid = m < args.M;
+            long long out_row = m;
+            if (valid && args.idx != nullptr) {
+                const int b = m / args.k, j = m - b * args.k;
+                if (args.count != nullptr && j >= args.count[b]) valid = false;
+                if (valid) out_row = (long long)b * args.n_out_rows + args.idx[m];
+            }
+            s_row[row] = valid ? (int)out_row : -1;
         }
+        __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned): reconverge after the guarded lookups
+        GPF(4);
         mbar_wait(smem_u32(tmem_full_bar), 0);
+        GPF(1);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            uint32_t acc[32];
-            __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned): reconverge after the guarded stores
-            tmem_load_32x32(taddr + (uint32_t)c0, acc);
-            const int n = n0 + c0;
-            if (valid && n < args.n_feat) {
-            uint4 packed[4];
+        // phase 1: accumulator -> bias / activation -> 16-byte chunks in the staging tile.  Every MMA has retired, so
+        // the smem ring is dead and is reused; chunk c of row r sits at position (c & ~7) | ((c ^ r) & 7).
+        uint8_t* stage_row = smem + row * L::OUT_STRIDE;
+        auto convert = [&](const uint32_t* acc, int c0, int width) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                const int ng = n + g * 8;
-                float y[8];
+                if (g * 8 < width) {
+                    const int ng = n0 + c0 + g * 8;
+                    float y[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(acc[g * 8 + i]);
-                if (ng < args.n_feat) {
-                    if (args.bias != nullptr) {
-                        float bv[8];
-                        const uint4 braw = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(args.bias) + ng);
-                        if (args.is_bf16) unpack16<__nv_bfloat16>(braw, bv);
-                        else unpack16<__half>(braw, bv);
+                    for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(acc[g * 8 + i]);
+                    if (ng < args.n_feat) {
+                        if (args.bias != nullptr) {
+                            float bv[8];
+                            const uint4 braw = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(args.bias) + ng);
+                            if (args.is_bf16) unpack16<__nv_bfloat16>(braw, bv);
+                            else unpack16<__half>(braw, bv);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) y[i] += bv[i];
+                            for (int i = 0; i < 8; ++i) y[i] += bv[i];
+                        }
+                        if (args.act == ET_ACT_GELU) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) y[i] = gelu_erf(y[i]);
+                        }
                     }
-                    if (args.act == ET_ACT_GELU) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) y[i] = gelu_erf(y[i]);
-                    }
+                    const int c = (c0 >> 3) + g;
+                    st16(stage_row + (((c & ~7) | ((c ^ row) & 7)) << 4), args.is_bf16 ? pack16<__nv_bfloat16>(y) : pack16<__half>(y));
                 }
-                packed[g] = args.is_bf16 ? pack16<__nv_bfloat16>(y) : pack16<__half>(y);
             }
-            uint16_t* dst = static_cast<uint16_t*>(args.out) + out_row * args.ld_out + n;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-                if (n + g * 8 < args.n_feat) st16(dst + g * 8, packed[g]);
+        };
+        constexpr int HALF_N = BLOCK_N / 2;
+        const int cbeg = chalf * HALF_N;
+#pragma unroll 1
+        for (int c0 = cbeg; c0 + 32 <= cbeg + HALF_N; c0 += 32) {
+            uint32_t acc[32];
+            tmem_load_32x32(taddr + (uint32_t)c0, acc);
+            GPF(2);
+            convert(acc, c0, 32);
+            GPF(3);
+        }
+        if constexpr (HALF_N % 32 != 0) {
+            uint32_t acc[16];
+            tmem_load_32x16(taddr + (uint32_t)(cbeg + HALF_N - 16), acc);
+            GPF(2);
+            convert(acc, cbeg + HALF_N - 16, 16);
+            GPF(3);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // staging tile and row table complete (epilogue warps only)
+        GPF(5);
+        // phase 2: a warp writes whole output rows: LPR lanes x 16 bytes are one row's BLOCK_N columns
+        constexpr int LPR = BLOCK_N / 8;
+        constexpr int RPI = 32 / LPR > 0 ? 32 / LPR : 1;  // rows per warp-wide store
+        const int sub = lane / LPR, c = lane % LPR;
+        const int n = n0 + c * 8;
+        uint16_t* out = static_cast<uint16_t*>(args.out);
+#pragma unroll 4
+        for (int it = 0; it < 16 / RPI; ++it) {
+            const int r = ew * 16 + it * RPI + sub;
+            if (sub < RPI && n < args.n_feat) {
+                const int orow = s_row[r];
+                if (orow >= 0)
+                    st16(out + (size_t)orow * args.ld_out + n,
+                         ld16(smem + r * L::OUT_STRIDE + (((c & ~7) | ((c ^ r) & 7)) << 4)));
             }
         }
+        GPF(6);
+        if (warp == 2 && lane == 0) GPF_FLUSH(2);
     }
 
     tcgen05_fence_before();
@@ -231,6 +313,10 @@ int et_debug_set(int key, long long value) {
         g_attn_tc = value != 0;
         return ET_OK;
     }
+    if (key == 7) {
+        g_gemm_prof = reinterpret_cast<unsigned long long*>(value);
+        return ET_OK;
+    }
     if (key == 4) {
         g_tc_prof = reinterpret_cast<unsigned long long*>(value);
         return ET_OK;
@@ -261,6 +347,7 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
     a.bias = bias; a.out = out; a.idx = reinterpret_cast<const long long*>(idx); a.count = count; a.ld_out = ld_out;
     a.M = (int)M; a.K = (int)K; a.n_feat = (int)n_feat; a.act = act; a.k = (int)(idx ? k : 1);
     a.n_out_rows = (int)n_out_rows; a.is_bf16 = dtype == ET_BF16;
+    a.prof = g_gemm_prof;
 
     // Tile width: minimise waves(tiles over 148 SMs) x per-tile cost (~ BLOCK_N + fixed overhead).
     const int candidates[5] = {256, 192, 128, 96, 64};

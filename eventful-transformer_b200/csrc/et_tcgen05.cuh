@@ -70,6 +70,15 @@ __device__ __forceinline__ void tmem_load_32x32(uint32_t taddr, uint32_t (&r)[32
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_load_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // 16 lanes x (4 x 256 bit): the mma-fragment-shaped TMEM load.  Thread t receives, for column group n < 4,
 // r[4n], r[4n+1] = lane (t / 4), 32-bit columns 8n + 2 (t % 4), + 1 and r[4n+2], r[4n+3] = the same columns of lane
 // (t / 4) + 8.  `taddr` lane = 32 (warp % 4) or that + 16.  No wait inside: pair with tmem_wait_ld().
