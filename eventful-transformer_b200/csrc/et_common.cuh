@@ -169,9 +169,11 @@ static inline cudaStream_t et_stream(void* s) { return reinterpret_cast<cudaStre
 // which sets cudaLaunchAttributeProgrammaticStreamSerialization, so launch latency and CTA scheduling of kernel n+1
 // overlap the tail of kernel n.  Opt-in with EVENTFUL_B200_PDL=1: measured on B200 it gains nothing under CUDA-graph
 // replay (265 vs 273 frames/s), where launches are already back to back.
+__device__ __forceinline__ void et_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void et_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void et_pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    et_pdl_trigger();
+    et_pdl_wait();
 }
 extern int g_et_pdl;
 template <typename... KArgs, typename... Args>

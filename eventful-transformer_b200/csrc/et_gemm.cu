@@ -78,7 +78,9 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                       const LinearArgs args) {
-    et_pdl_prologue();
+    // Programmatic dependent launch: everything that does not depend on the previous kernel (barrier / TMEM setup and
+    // the weight tiles of the first pipeline stages) runs before griddepcontrol.wait.
+    et_pdl_trigger();
     using L = GemmSmem<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
     extern __shared__ uint8_t smem_raw[];
@@ -120,7 +122,16 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_k_blocks; ++kb) {
+            const int pre = num_k_blocks < STAGES ? num_k_blocks : STAGES;
+            for (int kb = 0; kb < pre; ++kb) {  // weights are never written by a kernel: fetch them ahead of the wait
+                const uint32_t fb = smem_u32(&full_bar[kb]);
+                mbar_expect_tx(fb, L::STAGE_BYTES);
+                tma_load_2d(smem_u32(smem + kb * L::STAGE_BYTES) + A_TILE_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+            }
+            et_pdl_wait();
+            for (int kb = 0; kb < pre; ++kb)
+                tma_load_2d(smem_u32(smem + kb * L::STAGE_BYTES), &tmap_a, smem_u32(&full_bar[kb]), kb * BLOCK_K, m0);
+            for (int kb = pre; kb < num_k_blocks; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t parity = (kb / STAGES) & 1;
                 GPF(2);
@@ -162,6 +173,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
     } else {
         // ---- epilogue: warp w may only touch TMEM lanes [32 * (w % 4), +32)
+        et_pdl_wait();  // the index, the output rows and (through TMA) the activations belong to earlier kernels
         const int ew = warp - 2;
         const int quarter = warp & 3;
         const int chalf = ew >> 2;  // which half of the tile's columns this warp converts
