@@ -35,7 +35,8 @@ using namespace et_tc;
 // et_debug_set(6, 1): bracket the apply-kernel launch with CUDA events on its stream (bench.py reads the elapsed time
 // of the last launch through et_debug_elapsed_ms()); never enabled inside graph capture.
 int g_tc_time_apply = 0;
-// et_debug_set(4, device pointer to 4 x 16 u64): per-role cycle buckets of tc_apply_kernel, summed over all CTAs.
+// et_debug_set(4, device pointer to 8 x 16 u64): per-role cycle buckets, summed over all CTAs: rows 0-3 tc_apply_kernel
+// (producer, MMA, softmax, mover), rows 4-6 tc_stats_kernel (producer, MMA, softmax).
 // Only the profiling build (make prof: -DET_TC_PROFILE -> libeventful_b200_prof.so) writes to it.
 unsigned long long* g_tc_prof = nullptr;
 #ifdef ET_TC_PROFILE
@@ -137,24 +138,33 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
+            PF_DECL
             mbar_expect_tx(smem_u32(q_full), QROWS * 128);
             tma_load_2d(smem_u32(Qs), &tm_qkv, smem_u32(q_full), h * 64, b * a.N + q0);
             for (int t = 0; t < T; ++t) {
                 const int s = t % ST_STAGES;
+                PF(1);
                 mbar_wait(smem_u32(&k_empty[s]), ((t / ST_STAGES) & 1) ^ 1);
+                PF(0);
                 mbar_expect_tx(smem_u32(&k_full[s]), ST_TILE);
                 tma_load_2d(smem_u32(Ks + s * ST_TILE), &tm_qkv, smem_u32(&k_full[s]), a.D + h * 64, b * a.N + t * ST_KEYS);
             }
+            PF(1);
+            PF_FLUSH(4);
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_ex(128, ST_KEYS, a.is_bf16, 0);
+            PF_DECL
             mbar_wait(smem_u32(q_full), 0);
+            PF(7);
             const uint64_t dq = umma_smem_desc(smem_u32(Qs));
             for (int t = 0; t < T; ++t) {
                 const int s = t % ST_STAGES, u = t & 1;
                 mbar_wait(smem_u32(&k_full[s]), (t / ST_STAGES) & 1);
+                PF(0);
                 mbar_wait(smem_u32(&s_empty[u]), ((t >> 1) & 1) ^ 1);
+                PF(1);
                 tcgen05_fence_after();
                 const uint64_t dk = umma_smem_desc(smem_u32(Ks + s * ST_TILE));
 #pragma unroll
@@ -162,7 +172,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
                     tcgen05_mma_f16(tmem_base + u * ST_KEYS, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc, kk > 0);
                 tcgen05_commit(smem_u32(&k_empty[s]));
                 tcgen05_commit(smem_u32(&s_full[u]));
+                PF(2);
             }
+            PF_FLUSH(5);
         }
     } else {
         const int quarter = warp & 3;
@@ -192,8 +204,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
         }
         float m2 = -1e30f, l = 0.f;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        PF_DECL
         for (int t = 0; t < T; ++t) {
             const int u = t & 1;
+            PF(3);
             float bh2[2] = {0.f, 0.f};
             if (a.has_bias) {  // a 128-key tile spans two image rows of the 64-wide grid
                 const uint32_t pair = *reinterpret_cast<const uint32_t*>(bh_row + 2 * t);
@@ -201,6 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
                 bh2[1] = elem_to_float<BF16>((uint16_t)(pair >> 16)) * bscale;
             }
             mbar_wait(smem_u32(&s_full[u]), (t >> 1) & 1);
+            PF(0);
             tcgen05_fence_after();
             uint32_t v0[32], v1[32];
             tmem_load_32x32(taddr + (uint32_t)(u * ST_KEYS + half * 32), v0);       // image row 2t
@@ -208,6 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_empty[u]));
+            PF(1);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const uint32_t* v = c ? v1 : v0;
@@ -234,7 +250,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
                 }
                 l += sum0 + sum1;
             }
+            PF(2);
         }
+        PF(3);
+        if (lane == 0 && warp == 2) PF_FLUSH(6);
         // merge the two column halves of each row
         if (half == 1) xchg[row] = make_float2(m2, l);
         named_sync_softmax();

@@ -32,7 +32,7 @@ for order in ("ascending (what top-k emits)", "random"):
     blk.reset()
     blk._attention_first(qkv, None)
     for _ in range(3): blk._attention_incremental(qkv, idx)
-    prof = torch.zeros(4 * 16, dtype=torch.int64, device=dev)
+    prof = torch.zeros(8 * 16, dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
     native.lib().et_debug_set(4, prof.data_ptr())
     native.lib().et_debug_set(6, 1)
@@ -42,7 +42,7 @@ for order in ("ascending (what top-k emits)", "random"):
     native.lib().et_debug_set(4, 0)
     native.lib().et_debug_set(6, 0)
     ctas, tiles = (n // 128) * h, k // 64
-    v = prof.view(4, 16).tolist()
+    v = prof.view(8, 16).tolist()
     print(f"== index order: {order}; apply launch {ms * 1e3:.1f} us (profiling build); cycles per 64-key tile, mean over {ctas} CTAs")
     for role, (name, names) in ROLES.items():
         names = names or SM
