@@ -249,12 +249,14 @@ __device__ __forceinline__ void select_row(const GateArgs& a, int r, int* s_hist
             ie += te;
         }
     }
+    if (a.dbg != nullptr && tid == 0) a.dbg[6] = gtime();
     __syncthreads();
     if (lane == 31) {
         s_hist[64 + warp] = ig;
         s_hist[96 + warp] = ie;
     }
     __syncthreads();
+    if (a.dbg != nullptr && tid == 0) a.dbg[7] = gtime();
     int bg = 0, be = 0, n_greater = 0;
 #pragma unroll
     for (int w = 0; w < kGateThreads / 32; ++w) {
@@ -266,20 +268,20 @@ __device__ __forceinline__ void select_row(const GateArgs& a, int r, int* s_hist
     }
     remaining = a.k - n_greater;  // ties taken (equals the search's residual count)
     int pg = bg + ig - cg, pe = be + ie - ce;
-    auto emit = [&](int i, uint32_t key) {
-        if (key > kth) {
-            out[pg++] = i;
-        } else if (key == kth) {
-            if (pe < remaining) out[n_greater + pe] = i;
-            ++pe;
-        }
+    // branch-free: one predicated store per key (divergent if / else chains cost ~3 us here)
+    auto emit = [&](int i, uint32_t key, bool on) {
+        const bool g = on && key > kth, e = on && key == kth;
+        const int slot_i = g ? pg : n_greater + pe;
+        const bool take = g || (e && pe < remaining);
+        pg += g ? 1 : 0;
+        pe += e ? 1 : 0;
+        if (take) out[slot_i] = i;
     };
     if (in_regs) {  // static indices only: the key array must stay in registers
 #pragma unroll
-        for (int j = 0; j < KPT; ++j)
-            if (lo + j < hi) emit(lo + j, keys[j] & mask);
+        for (int j = 0; j < KPT; ++j) emit(lo + j, keys[j] & mask, lo + j < hi);
     } else {
-        for (int i = lo; i < hi; ++i) emit(i, order_key(__ldcg(norm + i)) & mask);
+        for (int i = lo; i < hi; ++i) emit(i, order_key(__ldcg(norm + i)) & mask, true);
     }
 }
 

@@ -21,6 +21,6 @@ for (B, N, D, k) in [(1, 4096, 768, 2048), (1, 1024, 768, 512), (4, 4096, 768, 2
         torch.cuda.synchronize()
         native.lib().et_debug_set(3, 0)
         d = dbg.tolist(); t0 = d[0]
-        rows.append([round((v - t0) / 1e3, 2) for v in d[1:6]] + [round(e0.elapsed_time(e1) * 1e3, 1)])
-    print((B, N, D, k), "us since first CTA start: [norm phase done (max), select start, keys loaded, search done, end] event_us")
+        rows.append([round((v - t0) / 1e3, 2) for v in (d[1], d[2], d[3], d[4], d[6], d[7], d[5])] + [round(e0.elapsed_time(e1) * 1e3, 1)])
+    print((B, N, D, k), "us since first CTA start: [norm phase done (max), select start, keys loaded, search done, counted+scanned, offsets known, end] event_us")
     for r in rows[2:]: print("   ", r)
