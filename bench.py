@@ -6,7 +6,8 @@ bench.py -- ViTDet-B Eventful backbone throughput on B200 (BASELINE.json metric)
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
     (N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
 
-A step = one incremental frame (t >= 1) of every stream of the rank through ViTBackbone.forward:
+A step = one incremental frame (t >= 1) of every stream of the rank (default 8 concurrent streams per GPU, batched
+along B; `single_stream` in the JSON line is the one-stream latency case) through ViTBackbone.forward:
 ViTDet-B, 1024x1024 input -> 4096 tokens, TokenNormTopK k = 2048, windowed EventfulTokenwiseBlock x8 +
 global EventfulBlock x4, bf16, random-init weights, synthetic token video x_t = x_0 + 0.1 t eps_t.
 Streams are independent (own gate state): ranks shard streams, no collective in the hot path
@@ -42,8 +43,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("ET_BENCH_STREAMS", "1")),
-                    help="video streams per GPU (batched along B)")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("ET_BENCH_STREAMS", "8")),
+                    help="concurrent video streams per GPU, batched along B (BASELINE configs[4]: 64 streams over 8 GPUs "
+                         "= 8 per GPU); the single-stream latency case is reported next to it as `single_stream`")
     ap.add_argument("--k", type=int, default=2048)
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--no-graph", action="store_true")
@@ -319,9 +321,11 @@ def kernel_leg(streams, n, d, k, grid, pk):
     lib.et_debug_set(6, 0)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-    if os.path.exists(tpath) and b == 1 and n == 4096 and k == 2048:
-        t = json.load(open(tpath))["tc_apply_kernel<bf16,DELTA>"]
-        traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    if os.path.exists(tpath) and n == 4096 and k == 2048:
+        table = json.load(open(tpath))
+        t = table.get("tc_apply_kernel<bf16,DELTA>" if b == 1 else f"tc_apply_kernel<bf16,DELTA>@{b}streams")
+        if t is not None:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     # algorithmic bytes: the selected A-gate state columns are read once and written once, 2 H N k e per stream
     add("tc_apply_kernel (A-gate + delta accumulate on tcgen05)", acc_ms / reps, 4, "hbm", b * 2.0 * h * n * k * e)
     out["tc_apply_kernel (A-gate + delta accumulate on tcgen05)"]["traffic"] = traffic
@@ -459,6 +463,17 @@ def main():
                          ms_per_step=round(ms_e2e / args.steps, 4)),
                 gpu_launches=int(per_step * args.steps), launches_per_step=int(per_step), clocks=clocks)
 
+    if rank == 0 and args.streams != 1:
+        # the latency case: ONE stream on this GPU (same model, own state), device-resident inputs, CUDA-graph replay
+        one = make_backbone(grid, "EventfulBlock", "EventfulTokenwiseBlock", args.k, dev, dt)
+        one_frames = [f[:1].contiguous() for f in frames_dev]
+        k1 = max(10, args.steps)
+        ms1, per1, _ = run_stream_model(one, one_frames, args.warmup, k1, None, use_graph)
+        line["single_stream"] = dict(value=round(k1 / (ms1 * 1e-3), 2), unit=UNIT, ms_per_frame=round(ms1 / k1, 4),
+                                     launches_per_step=int(per1), steps=k1)
+        del one, one_frames
+        torch.cuda.empty_cache()
+
     if rank == 0 and not args.quick:
         with torch.inference_mode():
             # dense comparators on the same GPU, same weights, same frames (single stream group)
@@ -487,7 +502,8 @@ def main():
                                 frac=kt["frac"], traffic=kt.get("traffic"),
                                 peak_source=pk["source"] + ", burst figure (kernel timed alone, L2 flushed, CUDA events "
                                             "on the launch stream)",
-                                traffic_source="ncu --set full, profiles/r1_ncu_tc_apply.csv (dram__bytes_read + write, one launch)",
+                                traffic_source="ncu --set full, profiles/r1_ncu_traffic.json <- r1_ncu_tc_apply*.csv (dram__bytes_read + write, "
+                                               "one launch at this stream count)",
                                 share_of_step=round(kt["ms"] * kt["per_step"] / (ms / args.steps), 3))
         line["kernels"] = kernels
         if world == 1:
