@@ -48,41 +48,51 @@ unsigned long long* g_gemm_prof = nullptr;
 #define GPF_FLUSH(role)
 #endif
 
-// GELU(x) = x Phi(x) with the exact-erf definition (torch.nn.GELU default).  erfc by Abramowitz-Stegun 7.1.26
-// (|error| < 1.5e-7, far below the 16-bit output rounding) on the FMA pipe plus two MUFU ops; libdevice's erff costs
-// ~40 instructions per element and made the mlp_1 epilogue longer than its mainloop.  Both tails are cancellation-free:
-// x Phi(x) = x (1 - q / 2) for x >= 0 and x q / 2 for x < 0, with q = erfc(|x| / sqrt 2).
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float q = poly * t * ex2_approx(-1.4426950408889634f * z * z);
-    return x * (x >= 0.f ? fmaf(-0.5f, q, 1.f) : 0.5f * q);
+// GELU(x) = x Phi(x) with the exact-erf definition (torch.nn.GELU default), two elements at a time.
+// Phi(x) = 1/2 + sign(x) (1/2 - q), q = erfc(|x| / sqrt 2) / 2 by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 on erf, far
+// below the 16-bit output rounding): q = (a1 t + ... + a5 t^5) / 2 * exp(-x^2 / 2), t = 1 / (1 + p |x| / sqrt 2).
+// Packed FFMA2 / FMUL2 arithmetic plus one rcp and one ex2 per element: ~9.5 issue slots per element, against ~22 for
+// the scalar version and ~40 for libdevice's erff (which made the mlp_1 epilogue three times longer than its mainloop).
+__device__ __forceinline__ void gelu_erf2(float& a, float& b) {
+    const float kc = 0.3275911f * 0.70710678118654752440f;
+    const f32x2 t = f2_pack(rcp_approx(fmaf(fabsf(a), kc, 1.f)), rcp_approx(fmaf(fabsf(b), kc, 1.f)));
+    const f32x2 x = f2_pack(a, b);
+    f32x2 p = f2_fma(f2_pack(0.5f * 1.061405429f, 0.5f * 1.061405429f), t, f2_pack(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+    p = f2_fma(p, t, f2_pack(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+    p = f2_fma(p, t, f2_pack(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+    p = f2_fma(p, t, f2_pack(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+    p = f2_mul(p, t);
+    float ea, eb;  // exp(-x^2 / 2) = exp2(x * x * (-log2(e) / 2))
+    f2_unpack(f2_mul(f2_mul(x, f2_pack(-0.72134752044448170368f, -0.72134752044448170368f)), x), ea, eb);
+    const f32x2 q = f2_mul(p, f2_pack(ex2_approx(ea), ex2_approx(eb)));
+    float sa, sb;  // 1/2 - q, carrying the sign of x
+    f2_unpack(f2_fma(q, f2_pack(-1.f, -1.f), f2_pack(0.5f, 0.5f)), sa, sb);
+    const f32x2 phi = f2_add(f2_pack(copysignf(sa, a), copysignf(sb, b)), f2_pack(0.5f, 0.5f));
+    f2_unpack(f2_mul(x, phi), a, b);
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MH>  // MH = 128-row halves per CTA tile (1 or 2): the halves share the W tile
 struct GemmSmem {
+    static constexpr int A_BYTES = MH * A_TILE_BYTES;
     static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
-    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_TILE_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int ROW_OFFSET = BAR_OFFSET + 256;     // int[128]: scatter target row of every tile row
+    static constexpr int ROW_OFFSET = BAR_OFFSET + 256;     // int[128]: scatter target row of every row of a half
     static constexpr int TOTAL = ROW_OFFSET + 512 + 1024;   // barriers + row table + alignment slack
     static constexpr int OUT_STRIDE = (BLOCK_N * 2 + 127) / 128 * 128;  // staging tile row pitch (whole swizzle groups)
     static_assert(BLOCK_M * OUT_STRIDE <= STAGES * STAGE_BYTES, "epilogue staging tile must fit in the smem ring");
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MH>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                       const LinearArgs args) {
     // Programmatic dependent launch: everything that does not depend on the previous kernel (barrier / TMEM setup and
     // the weight tiles of the first pipeline stages) runs before griddepcontrol.wait.
     et_pdl_trigger();
-    using L = GemmSmem<BLOCK_N, STAGES>;
-    constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+    using L = GemmSmem<BLOCK_N, STAGES, MH>;
+    constexpr int ACC_COLS = MH * BLOCK_N;  // accumulator of half h: columns [h * BLOCK_N, +BLOCK_N)
+    constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -95,7 +105,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BLOCK_N;
-    const int m0 = blockIdx.y * BLOCK_M;
+    const int m0 = blockIdx.y * (BLOCK_M * MH);
     const int num_k_blocks = (args.K + BLOCK_K - 1) / BLOCK_K;
 
     if (warp == 0 && lane == 0) {
@@ -126,7 +136,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             for (int kb = 0; kb < pre; ++kb) {  // weights are never written by a kernel: fetch them ahead of the wait
                 const uint32_t fb = smem_u32(&full_bar[kb]);
                 mbar_expect_tx(fb, L::STAGE_BYTES);
-                tma_load_2d(smem_u32(smem + kb * L::STAGE_BYTES) + A_TILE_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+                tma_load_2d(smem_u32(smem + kb * L::STAGE_BYTES) + L::A_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
             }
             et_pdl_wait();
             for (int kb = 0; kb < pre; ++kb)
@@ -141,7 +151,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 const uint32_t fb = smem_u32(&full_bar[s]);
                 mbar_expect_tx(fb, L::STAGE_BYTES);
                 tma_load_2d(a_dst, &tmap_a, fb, kb * BLOCK_K, m0);
-                tma_load_2d(a_dst + A_TILE_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+                tma_load_2d(a_dst + L::A_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
             }
             GPF(2);
             GPF_FLUSH(0);
@@ -157,13 +167,16 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 if (kb == 0) GPF(3); else GPF(1);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-                const uint64_t da = umma_smem_desc(a_addr);
-                const uint64_t db = umma_smem_desc(a_addr + A_TILE_BYTES);
+                const uint64_t db = umma_smem_desc(a_addr + L::A_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-                    // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-                    tcgen05_mma_f16(tmem_base, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc,
-                                    (kb > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int hh = 0; hh < MH; ++hh) {  // the 128-row halves alternate: two independent accumulators
+                        const uint64_t da = umma_smem_desc(a_addr + hh * A_TILE_BYTES);
+                        // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+                        tcgen05_mma_f16(tmem_base + hh * BLOCK_N, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc,
+                                        (kb > 0 || kk > 0) ? 1u : 0u);
+                    }
                 }
                 tcgen05_commit(smem_u32(&empty_bar[s]));  // frees the smem stage once these MMAs retire
             }
@@ -178,8 +191,12 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int quarter = warp & 3;
         const int chalf = ew >> 2;  // which half of the tile's columns this warp converts
         const int row = quarter * 32 + lane;
-        const int m = m0 + row;
         int* s_row = reinterpret_cast<int*>(smem + L::ROW_OFFSET);
+        uint16_t* out = static_cast<uint16_t*>(args.out);
+#pragma unroll 1
+        for (int hh = 0; hh < MH; ++hh) {
+        const int m = m0 + hh * BLOCK_M + row;
+        if (hh > 0) asm volatile("bar.sync 1, 256;" ::: "memory");  // staging tile and row table of the previous half are read
         if (chalf == 0) {
             bool valid = m < args.M;
             long long out_row = m;
@@ -192,10 +209,10 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
         __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned): reconverge after the guarded lookups
         GPF(4);
-        mbar_wait(smem_u32(tmem_full_bar), 0);
+        if (hh == 0) mbar_wait(smem_u32(tmem_full_bar), 0);
         GPF(1);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(hh * BLOCK_N);
         // phase 1: accumulator -> bias / activation -> 16-byte chunks in the staging tile.  Every MMA has retired, so
         // the smem ring is dead and is reused; chunk c of row r sits at position (c & ~7) | ((c ^ r) & 7).
         uint8_t* stage_row = smem + row * L::OUT_STRIDE;
@@ -218,7 +235,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                         }
                         if (args.act == ET_ACT_GELU) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) y[i] = gelu_erf(y[i]);
+                            for (int i = 0; i < 8; i += 2) gelu_erf2(y[i], y[i + 1]);
                         }
                     }
                     const int c = (c0 >> 3) + g;
@@ -250,7 +267,6 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         constexpr int RPI = 32 / LPR > 0 ? 32 / LPR : 1;  // rows per warp-wide store
         const int sub = lane / LPR, c = lane % LPR;
         const int n = n0 + c * 8;
-        uint16_t* out = static_cast<uint16_t*>(args.out);
 #pragma unroll 4
         for (int it = 0; it < 16 / RPI; ++it) {
             const int r = ew * 16 + it * RPI + sub;
@@ -262,6 +278,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
         }
         GPF(6);
+        }  // halves
         if (warp == 2 && lane == 0) GPF_FLUSH(2);
     }
 
@@ -275,27 +292,28 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 }
 
 // ---------------------------------------------------------------- host side
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MH = 1>
 int launch_linear(const void* A, const void* W, const LinearArgs& args, cudaStream_t stream) {
-    using L = GemmSmem<BLOCK_N, STAGES>;
+    using L = GemmSmem<BLOCK_N, STAGES, MH>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(linear_tcgen05_kernel<BLOCK_N, STAGES>,
+        cudaError_t e = cudaFuncSetAttribute(linear_tcgen05_kernel<BLOCK_N, STAGES, MH>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
         if (e != cudaSuccess) return et_fail(ET_ERR_CUDA, "et_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     CUtensorMap ta, tw;
-    int rc = make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M, args.is_bf16);
+    int rc = make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M * MH, args.is_bf16);
     if (rc) return rc;
     rc = make_tmap_2d(&tw, W, args.n_feat, args.K, BLOCK_N, args.is_bf16);
     if (rc) return rc;
-    dim3 grid((args.n_feat + BLOCK_N - 1) / BLOCK_N, (args.M + BLOCK_M - 1) / BLOCK_M);
-    et_launch(linear_tcgen05_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kGemmThreads), L::TOTAL, stream, ta, tw, args);
+    dim3 grid((args.n_feat + BLOCK_N - 1) / BLOCK_N, (args.M + BLOCK_M * MH - 1) / (BLOCK_M * MH));
+    et_launch(linear_tcgen05_kernel<BLOCK_N, STAGES, MH>, dim3(grid), dim3(kGemmThreads), L::TOTAL, stream, ta, tw, args);
     ET_COUNT_LAUNCH(1);
     return ET_OK;
 }
 
+int g_force_mh = 0;  // et_debug_set(8, 1 | 2): rows per CTA tile = 128 x value (0 = auto)
 int g_force_block_n = 0;
 int g_force_depth = 0;  // test / tuning hook: et_debug_set(5, 1 = deep pipelines, 2 = shallow (two CTAs per SM), 0 = auto)  // test hook: et_debug_set(1, BLOCK_N)
 
@@ -319,6 +337,10 @@ int et_debug_set(int key, long long value) {
     }
     if (key == 5) {
         g_force_depth = (int)value;
+        return ET_OK;
+    }
+    if (key == 8) {
+        g_force_mh = (int)value;
         return ET_OK;
     }
     if (key == 2) {
@@ -382,6 +404,20 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
     // tiles is a single wave).  Shallow is used when the tile count exceeds one CTA-per-SM wave.
     const long long tiles_best = mt * ((n_feat + best - 1) / best);
     const bool shallow = g_force_depth ? g_force_depth == 2 : tiles_best > 148;
+    // 256-row CTA tiles (two 128-row accumulators sharing one W tile, one CTA per SM): a third less operand traffic from
+    // L2, but no second CTA whose mainloop hides the epilogue.  Measured (profiles/r1_gemm_sweep.txt): only long-K
+    // layers of multi-stream batches gain (mlp_2 at M = 16384: 84 -> 80 us); everything else keeps 128-row tiles.
+    int mh = g_force_mh;
+    int bn2 = best >= 192 ? best : 192;
+    if (g_force_block_n) bn2 = g_force_block_n;
+    if (mh == 0) mh = (K >= 2048 && ((M + 255) / 256) * ((n_feat + bn2 - 1) / bn2) >= 4 * 148) ? 2 : 1;
+    if (mh == 2 && (bn2 == 128 || bn2 == 192 || bn2 == 256)) {
+        switch (bn2) {
+            case 128: rc = launch_linear<128, 2, 2>(A, W, a, s); break;
+            case 192: rc = launch_linear<192, 3, 2>(A, W, a, s); break;
+            default: rc = launch_linear<256, 3, 2>(A, W, a, s); break;
+        }
+    } else
     switch (best) {
         case 256: rc = shallow ? launch_linear<256, 2>(A, W, a, s) : launch_linear<256, 4>(A, W, a, s); break;
         case 192: rc = shallow ? launch_linear<192, 2>(A, W, a, s) : launch_linear<192, 5>(A, W, a, s); break;
