@@ -78,7 +78,8 @@ struct GemmSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_TILE_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int ROW_OFFSET = BAR_OFFSET + 256;     // int[128]: scatter target row of every row of a half
-    static constexpr int TOTAL = ROW_OFFSET + 512 + 1024;   // barriers + row table + alignment slack
+    static constexpr int BIAS_OFFSET = ROW_OFFSET + 512;    // the tile's BLOCK_N bias values (16-bit)
+    static constexpr int TOTAL = BIAS_OFFSET + 512 + 1024;  // barriers + row table + bias + alignment slack
     static constexpr int OUT_STRIDE = (BLOCK_N * 2 + 127) / 128 * 128;  // staging tile row pitch (whole swizzle groups)
     static_assert(BLOCK_M * OUT_STRIDE <= STAGES * STAGE_BYTES, "epilogue staging tile must fit in the smem ring");
 };
@@ -192,7 +193,17 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int chalf = ew >> 2;  // which half of the tile's columns this warp converts
         const int row = quarter * 32 + lane;
         int* s_row = reinterpret_cast<int*>(smem + L::ROW_OFFSET);
+        uint16_t* s_bias = reinterpret_cast<uint16_t*>(smem + L::BIAS_OFFSET);
         uint16_t* out = static_cast<uint16_t*>(args.out);
+        // the tile's bias slice goes to shared memory once (a global load per 8 columns in the conversion loop exposed its
+        // latency 12-16 times per thread)
+        if (args.bias != nullptr && (int)threadIdx.x - 64 < BLOCK_N / 8) {
+            const int t8 = ((int)threadIdx.x - 64) * 8;
+            *reinterpret_cast<uint4*>(s_bias + t8) =
+                n0 + t8 < args.n_feat ? *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(args.bias) + n0 + t8)
+                                      : make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
         for (int hh = 0; hh < MH; ++hh) {
         const int m = m0 + hh * BLOCK_M + row;
@@ -227,7 +238,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     if (ng < args.n_feat) {
                         if (args.bias != nullptr) {
                             float bv[8];
-                            const uint4 braw = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(args.bias) + ng);
+                            const uint4 braw = *reinterpret_cast<const uint4*>(s_bias + c0 + g * 8);
                             if (args.is_bf16) unpack16<__nv_bfloat16>(braw, bv);
                             else unpack16<__half>(braw, bv);
 #pragma unroll
@@ -291,6 +302,250 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent variant for multi-wave problems (multi-stream batches): one CTA per SM walks over 128 x BLOCK_N output
+// tiles (n fastest, so the CTAs of a wave share A rows and keep W resident in L2).  The smem ring runs across tile
+// boundaries (the producer is already loading tile i+1 while tile i is multiplied), the accumulator is double buffered
+// in TMEM (2 x BLOCK_N columns) and the epilogue of tile i overlaps the mainloop of tile i+1 inside the same CTA;
+// barrier / TMEM / tensor-map setup is paid once per CTA instead of once per tile.
+// ------------------------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES>
+struct PersistSmem {
+    static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int OUT_STRIDE = (BLOCK_N * 2 + 127) / 128 * 128;
+    static constexpr int STAGE_OFFSET = STAGES * STAGE_BYTES;          // epilogue staging tile (the ring stays live)
+    static constexpr int BAR_OFFSET = STAGE_OFFSET + BLOCK_M * OUT_STRIDE;
+    static constexpr int ROW_OFFSET = BAR_OFFSET + 256;
+    static constexpr int BIAS_OFFSET = ROW_OFFSET + 512;
+    static constexpr int TOTAL = BIAS_OFFSET + 512 + 1024;
+    static_assert(TOTAL <= 227 * 1024, "persistent GEMM tile does not fit in shared memory");
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                         const LinearArgs args) {
+    et_pdl_trigger();
+    using L = PersistSmem<BLOCK_N, STAGES>;
+    constexpr int TMEM_COLS = 2 * BLOCK_N <= 256 ? 256 : 512;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;       // [2] accumulator buffer complete (MMA -> epilogue)
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2] accumulator buffer drained (8 epilogue warps -> MMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_k_blocks = (args.K + BLOCK_K - 1) / BLOCK_K;
+    const int n_tiles = (args.n_feat + BLOCK_N - 1) / BLOCK_N;
+    const int m_tiles = (args.M + BLOCK_M - 1) / BLOCK_M;
+    const int num_tiles = n_tiles * m_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int u = 0; u < 2; ++u) {
+            mbar_init(smem_u32(&tmem_full[u]), 1);
+            mbar_init(smem_u32(&tmem_empty[u]), 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            et_pdl_wait();
+            GPF_DECL
+            int kbg = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++kbg) {
+                    const int s = kbg % STAGES;
+                    GPF(2);
+                    mbar_wait(smem_u32(&empty_bar[s]), ((kbg / STAGES) & 1) ^ 1);
+                    GPF(1);
+                    const uint32_t dst = smem_u32(smem + s * L::STAGE_BYTES);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(fb, L::STAGE_BYTES);
+                    tma_load_2d(dst, &tmap_a, fb, kb * BLOCK_K, m0);
+                    tma_load_2d(dst + A_TILE_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+                }
+            }
+            GPF(2);
+            GPF_FLUSH(0);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(BLOCK_N, args.is_bf16);
+            int kbg = 0, it = 0;
+            GPF_DECL
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                GPF(2);
+                mbar_wait(smem_u32(&tmem_empty[buf]), ((it >> 1) & 1) ^ 1);  // epilogue of tile it - 2 has drained it
+                GPF(3);
+                tcgen05_fence_after();
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++kbg) {
+                    const int s = kbg % STAGES;
+                    GPF(2);
+                    mbar_wait(smem_u32(&full_bar[s]), (kbg / STAGES) & 1);
+                    GPF(1);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                    const uint64_t da = umma_smem_desc(a_addr);
+                    const uint64_t db = umma_smem_desc(a_addr + A_TILE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                        tcgen05_mma_f16(tmem_base + buf * BLOCK_N, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc,
+                                        (kb > 0 || kk > 0) ? 1u : 0u);
+                    tcgen05_commit(smem_u32(&empty_bar[s]));
+                }
+                tcgen05_commit(smem_u32(&tmem_full[buf]));
+            }
+            GPF(2);
+            GPF_FLUSH(1);
+        }
+    } else {
+        et_pdl_wait();
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int chalf = ew >> 2;
+        const int row = quarter * 32 + lane;
+        int* s_row = reinterpret_cast<int*>(smem + L::ROW_OFFSET);
+        uint8_t* stage = smem + L::STAGE_OFFSET;
+        uint8_t* stage_row = stage + row * L::OUT_STRIDE;
+        uint16_t* out = static_cast<uint16_t*>(args.out);
+        uint16_t* s_bias = reinterpret_cast<uint16_t*>(smem + L::BIAS_OFFSET);
+        auto load_bias = [&](int tile) {  // the tile's bias slice -> shared memory (read back as broadcast LDS.128)
+            const int t8 = ((int)threadIdx.x - 64) * 8;
+            if (args.bias != nullptr && tile < num_tiles && t8 < BLOCK_N) {
+                const int ng = (tile % n_tiles) * BLOCK_N + t8;
+                *reinterpret_cast<uint4*>(s_bias + t8) =
+                    ng < args.n_feat ? *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(args.bias) + ng)
+                                     : make_uint4(0, 0, 0, 0);
+            }
+        };
+        load_bias(blockIdx.x);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        int it = 0;
+        GPF_DECL
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            const int m = m0 + row;
+            GPF(6);
+            if (chalf == 0) {
+                bool valid = m < args.M;
+                long long out_row = m;
+                if (valid && args.idx != nullptr) {
+                    const int b = m / args.k, j = m - b * args.k;
+                    if (args.count != nullptr && j >= args.count[b]) valid = false;
+                    if (valid) out_row = (long long)b * args.n_out_rows + args.idx[m];
+                }
+                s_row[row] = valid ? (int)out_row : -1;
+            }
+            __syncwarp();
+            GPF(4);
+            mbar_wait(smem_u32(&tmem_full[buf]), (it >> 1) & 1);
+            GPF(1);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BLOCK_N);
+            auto convert = [&](const uint32_t* acc, int c0, int width) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g * 8 < width) {
+                        const int ng = n0 + c0 + g * 8;
+                        float y[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(acc[g * 8 + i]);
+                        if (ng < args.n_feat) {
+                            if (args.bias != nullptr) {
+                                float bv[8];
+                                const uint4 braw = *reinterpret_cast<const uint4*>(s_bias + c0 + g * 8);
+                                if (args.is_bf16) unpack16<__nv_bfloat16>(braw, bv);
+                                else unpack16<__half>(braw, bv);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) y[i] += bv[i];
+                            }
+                            if (args.act == ET_ACT_GELU) {
+#pragma unroll
+                                for (int i = 0; i < 8; i += 2) gelu_erf2(y[i], y[i + 1]);
+                            }
+                        }
+                        const int c = (c0 >> 3) + g;
+                        st16(stage_row + (((c & ~7) | ((c ^ row) & 7)) << 4),
+                             args.is_bf16 ? pack16<__nv_bfloat16>(y) : pack16<__half>(y));
+                    }
+                }
+            };
+            constexpr int HALF_N = BLOCK_N / 2;
+            const int cbeg = chalf * HALF_N;
+#pragma unroll 1
+            for (int c0 = cbeg; c0 + 32 <= cbeg + HALF_N; c0 += 32) {
+                uint32_t acc[32];
+                tmem_load_32x32(taddr + (uint32_t)c0, acc);
+                if (c0 + 64 > cbeg + HALF_N && HALF_N % 32 == 0) {  // last read of this buffer: hand it back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf]));
+                }
+                convert(acc, c0, 32);
+            }
+            if constexpr (HALF_N % 32 != 0) {
+                uint32_t acc[16];
+                tmem_load_32x16(taddr + (uint32_t)(cbeg + HALF_N - 16), acc);
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf]));
+                convert(acc, cbeg + HALF_N - 16, 16);
+            }
+            GPF(3);
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // staging tile and row table complete, bias slice consumed
+            GPF(5);
+            load_bias(tile + (int)gridDim.x);  // next tile's slice; visible after the trailing barrier
+            constexpr int LPR = BLOCK_N / 8;
+            constexpr int RPI = 32 / LPR > 0 ? 32 / LPR : 1;
+            constexpr int NIT = 16 / RPI;
+            const int sub = lane / LPR, c = lane % LPR;
+            const int n = n0 + c * 8;
+            // all shared-memory reads first, then the stores: one latency instead of NIT
+            uint4 rowv[NIT];
+            int orow[NIT];
+#pragma unroll
+            for (int r_it = 0; r_it < NIT; ++r_it) {
+                const int r = ew * 16 + r_it * RPI + (sub < RPI ? sub : 0);
+                orow[r_it] = (sub < RPI && n < args.n_feat) ? s_row[r] : -1;
+                rowv[r_it] = ld16(stage + r * L::OUT_STRIDE + (((c & ~7) | ((c ^ r) & 7)) << 4));
+            }
+#pragma unroll
+            for (int r_it = 0; r_it < NIT; ++r_it)
+                if (orow[r_it] >= 0) st16(out + (size_t)orow[r_it] * args.ld_out + n, rowv[r_it]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // staging tile and row table may be rewritten
+        }
+        GPF(6);
+        if (warp == 2 && lane == 0) GPF_FLUSH(2);
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------- host side
 template <int BLOCK_N, int STAGES, int MH = 1>
 int launch_linear(const void* A, const void* W, const LinearArgs& args, cudaStream_t stream) {
@@ -313,6 +568,31 @@ int launch_linear(const void* A, const void* W, const LinearArgs& args, cudaStre
     return ET_OK;
 }
 
+template <int BLOCK_N, int STAGES>
+int launch_persistent(const void* A, const void* W, const LinearArgs& args, cudaStream_t stream) {
+    using L = PersistSmem<BLOCK_N, STAGES>;
+    static int sms = 0;
+    if (sms == 0) {
+        cudaError_t e = cudaFuncSetAttribute(linear_persistent_kernel<BLOCK_N, STAGES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        if (e != cudaSuccess) return et_fail(ET_ERR_CUDA, "et_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    CUtensorMap ta, tw;
+    int rc = make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M, args.is_bf16);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tw, W, args.n_feat, args.K, BLOCK_N, args.is_bf16);
+    if (rc) return rc;
+    const long long tiles = (long long)((args.n_feat + BLOCK_N - 1) / BLOCK_N) * ((args.M + BLOCK_M - 1) / BLOCK_M);
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    et_launch(linear_persistent_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kGemmThreads), L::TOTAL, stream, ta, tw, args);
+    ET_COUNT_LAUNCH(1);
+    return ET_OK;
+}
+
+int g_force_persist = 0;  // et_debug_set(9, 1 = always persistent, 2 = never, 0 = auto)
 int g_force_mh = 0;  // et_debug_set(8, 1 | 2): rows per CTA tile = 128 x value (0 = auto)
 int g_force_block_n = 0;
 int g_force_depth = 0;  // test / tuning hook: et_debug_set(5, 1 = deep pipelines, 2 = shallow (two CTAs per SM), 0 = auto)  // test hook: et_debug_set(1, BLOCK_N)
@@ -341,6 +621,10 @@ int et_debug_set(int key, long long value) {
     }
     if (key == 8) {
         g_force_mh = (int)value;
+        return ET_OK;
+    }
+    if (key == 9) {
+        g_force_persist = (int)value;
         return ET_OK;
     }
     if (key == 2) {
@@ -407,10 +691,27 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
     // 256-row CTA tiles (two 128-row accumulators sharing one W tile, one CTA per SM): a third less operand traffic from
     // L2, but no second CTA whose mainloop hides the epilogue.  Measured (profiles/r1_gemm_sweep.txt): only long-K
     // layers of multi-stream batches gain (mlp_2 at M = 16384: 84 -> 80 us); everything else keeps 128-row tiles.
+    // persistent kernel: multi-wave problems (at least two waves of 128 x 256 tiles); measured in profiles/r1_gemm_sweep.txt
+    {
+        const int pbn = g_force_block_n == 128 || g_force_block_n == 192 ? g_force_block_n : 256;
+        const long long ptiles = mt * ((n_feat + pbn - 1) / pbn);
+        const bool long_k = K >= 2048;  // long-K layers do better with 256-row tiles (below)
+        const bool persist = g_force_persist ? g_force_persist == 1 : (ptiles >= 2 * 148 && g_force_mh == 0 && !long_k);
+        if (persist) {
+            switch (pbn) {
+                case 128: rc = launch_persistent<128, 5>(A, W, a, s); break;
+                case 192: rc = launch_persistent<192, 4>(A, W, a, s); break;
+                default: rc = launch_persistent<256, 3>(A, W, a, s); break;
+            }
+            if (rc) return rc;
+            ET_CHECK_LAUNCH("et_linear");
+            return ET_OK;
+        }
+    }
     int mh = g_force_mh;
     int bn2 = best >= 192 ? best : 192;
     if (g_force_block_n) bn2 = g_force_block_n;
-    if (mh == 0) mh = (K >= 2048 && ((M + 255) / 256) * ((n_feat + bn2 - 1) / bn2) >= 4 * 148) ? 2 : 1;
+    if (mh == 0) mh = (K >= 2048 && ((M + 255) / 256) * ((n_feat + bn2 - 1) / bn2) >= 128) ? 2 : 1;
     if (mh == 2 && (bn2 == 128 || bn2 == 192 || bn2 == 256)) {
         switch (bn2) {
             case 128: rc = launch_linear<128, 2, 2>(A, W, a, s); break;

@@ -10,9 +10,10 @@ from eventful_transformer import _native as native
 dev, dt = "cuda", torch.bfloat16
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 NAMES = {0: ("TMA producer", {0: "prologue", 1: "wait empty slot", 2: "issue TMA"}),
-         1: ("MMA issuer", {0: "prologue", 3: "wait first stage", 1: "wait full stage", 2: "issue MMAs"}),
+         1: ("MMA issuer", {0: "prologue", 3: "wait first stage / (persistent) accumulator buffer", 1: "wait full stage", 2: "issue MMAs"}),
          2: ("epilogue warp 2", {0: "prologue", 4: "index lookup", 1: "wait accumulator", 2: "tcgen05.ld", 3: "bias/act/pack -> staging", 5: "staging barrier", 6: "row stores"})}
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+if len(sys.argv) > 2: native.lib().et_debug_set(9, int(sys.argv[2]))  # 1 = persistent kernel
 for name, K, F, act in (("qkv", 768, 2304, 0), ("proj", 768, 768, 0), ("mlp1", 768, 3072, 1), ("mlp2", 3072, 768, 0)):
     x = torch.randn(M, K, device=dev).to(dt); w = (torch.randn(F, K, device=dev) * 0.02).to(dt); bias = torch.randn(F, device=dev).to(dt)
     out = torch.empty(M, F, device=dev, dtype=dt)

@@ -19,17 +19,23 @@ for M in (2048, 8192, 16384):
     x = torch.randn(M, K, device=dev).to(dt); w = (torch.randn(F, K, device=dev) * 0.02).to(dt); bias = torch.randn(F, device=dev).to(dt)
     out = torch.empty(M, F, device=dev, dtype=dt)
     res = {}
+    native.lib().et_debug_set(8, 1); native.lib().et_debug_set(9, 2)
     for bn in (0, 64, 96, 128, 192, 256):
         for depth in (1, 2):
             native.lib().et_debug_set(1, bn); native.lib().et_debug_set(5, depth)
             res[(bn, depth)] = round(t(lambda: native.linear(x, w, bias, act=act, out=out)), 1)
     native.lib().et_debug_set(5, 0)
+    native.lib().et_debug_set(9, 2)
     for bn in (128, 192, 256):  # 256-row CTA tiles (two accumulators share a W tile): reported as depth 3
         native.lib().et_debug_set(1, bn); native.lib().et_debug_set(8, 2)
         res[(bn, 3)] = round(t(lambda: native.linear(x, w, bias, act=act, out=out)), 1)
-    native.lib().et_debug_set(1, 0); native.lib().et_debug_set(8, 1)
+    native.lib().et_debug_set(8, 0); native.lib().et_debug_set(9, 1)
+    for bn in (128, 192, 256):  # persistent kernel (ring across tiles, double-buffered TMEM): reported as depth 4
+        native.lib().et_debug_set(1, bn)
+        res[(bn, 4)] = round(t(lambda: native.linear(x, w, bias, act=act, out=out)), 1)
+    native.lib().et_debug_set(1, 0); native.lib().et_debug_set(8, 1); native.lib().et_debug_set(9, 2)
     auto1 = round(t(lambda: native.linear(x, w, bias, act=act, out=out)), 1)
-    native.lib().et_debug_set(8, 0)
+    native.lib().et_debug_set(8, 0); native.lib().et_debug_set(9, 0)
     auto = round(t(lambda: native.linear(x, w, bias, act=act, out=out)), 1)
     ref = round(t(lambda: torch.nn.functional.linear(x, w, bias)), 1)
     fl = 2.0 * M * K * F

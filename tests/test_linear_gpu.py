@@ -58,6 +58,37 @@ def test_linear_every_tile_width(block_n):
 
 
 @pytest.mark.parametrize("block_n", [128, 192, 256])
+def test_linear_persistent_kernel(block_n):
+    """The persistent multi-wave kernel (ring across tiles, double-buffered TMEM accumulator), forced for every shape:
+    fewer tiles than SMs, many tiles per CTA, ragged M / N, GELU, scatter epilogue; repeated launches."""
+    dtype = torch.bfloat16
+    try:
+        native.lib().et_debug_set(1, block_n)
+        native.lib().et_debug_set(9, 1)
+        for m, k, f in [(2048, 768, 2304), (257, 72, 136), (100, 64, 64), (640, 3072, 768), (16384, 768, 3072),
+                        (16384, 3072, 768), (5000, 768, 2304)]:
+            x, w, b = make(m, k, f, dtype, seed=block_n + m)
+            for _ in range(2):
+                check(native.linear(x, w, b), reference(x, w, b, 0), dtype)
+            check(native.linear(x, w, None, act=1), reference(x, w, None, 1), dtype)
+        batch, n, k_sel, kdim, f = 8, 4096, 2048, 768, 768
+        x, w, b = make(batch * k_sel, kdim, f, dtype, seed=9)
+        idx = torch.stack([torch.randperm(n, generator=torch.Generator().manual_seed(5 + i))[:k_sel] for i in range(batch)]).to(DEV)
+        buf = torch.full((batch, n, f), 7.0, dtype=dtype, device=DEV)
+        native.linear(x.view(batch, k_sel, kdim), w, b, out=buf, idx=idx)
+        native.lib().et_debug_set(9, 2)
+        native.lib().et_debug_set(8, 1)
+        dense = native.linear(x, w, b).view(batch, k_sel, f)
+        want = torch.full((batch, n, f), 7.0, dtype=dtype, device=DEV)
+        want.scatter_(1, idx.unsqueeze(-1).expand(-1, -1, f), dense)
+        assert torch.equal(buf, want)
+    finally:
+        native.lib().et_debug_set(1, 0)
+        native.lib().et_debug_set(8, 0)
+        native.lib().et_debug_set(9, 0)
+
+
+@pytest.mark.parametrize("block_n", [128, 192, 256])
 def test_linear_256_row_tiles(block_n):
     """Two 128-row accumulators per CTA sharing one W tile (the multi-stream configuration), forced for small shapes:
     ragged M (tail rows in the second half, or no second half at all), GELU, and the scatter epilogue."""
