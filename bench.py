@@ -410,7 +410,20 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its version banner to fd 1 when the communicator is created (whatever NCCL_DEBUG the launcher
+        # exported): point fd 1 at stderr until the first collective has run, so stdout carries the JSON line only
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device=torch.device("cuda", local))
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         dist_ctx = dist
     from eventful_transformer import _native as native
 

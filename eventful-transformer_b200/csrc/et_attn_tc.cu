@@ -98,7 +98,7 @@ constexpr int ST_OFF_X = QROWS * 128 + ST_STAGES * ST_TILE;  // (m2, l) exchange
 constexpr int ST_SMEM = ST_OFF_X + QROWS * 8 + 256 + 1024;
 
 template <bool BF16>
-__global__ void __launch_bounds__(kThreads, 2) tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const TcArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const TcArgs a) {
     et_pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
