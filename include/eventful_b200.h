@@ -98,7 +98,10 @@ int et_sub(const void* a, const void* b, void* out, int64_t n, int dtype, void* 
 /* Test / tuning / measurement hooks.  key 1: force the GEMM tile width BLOCK_N (0 = automatic); key 2: 0 routes
  * attention through the mma.sync kernels even where the tcgen05 kernels apply (1 = default); key 3: device pointer to
  * 8 x uint64 receiving %globaltimer phase stamps of et_gate_select (0 = off); key 5: GEMM pipeline depth (1 deep,
- * 2 shallow = two CTAs per SM, 0 = automatic); key 6: 1 brackets the global-attention apply kernel with CUDA events. */
+ * 2 shallow = two CTAs per SM, 0 = automatic); key 6: 1 brackets the global-attention apply kernel with CUDA events;
+ * key 4 / key 7: device pointer to 8 x 16 / 3 x 16 uint64 cycle buckets per warp role of the attention / GEMM kernels
+ * (written only by the profiling build, `make prof`); key 8: GEMM rows per CTA tile (1 = 128, 2 = 256, 0 = automatic);
+ * key 9: persistent GEMM kernel (1 = always, 2 = never, 0 = automatic). */
 int et_debug_set(int key, long long value);
 /* Milliseconds of the last apply-kernel launch bracketed under key 6 (synchronises on its end event). */
 float et_debug_elapsed_ms(void);
