@@ -88,24 +88,30 @@ __device__ __forceinline__ uint32_t pack2_elem(float lo, float hi) {  // one F2F
     return r;
 }
 
+__device__ __forceinline__ void tmem_load_cols(uint32_t taddr, uint32_t (&r)[32]) { tmem_load_32x32(taddr, r); }
+__device__ __forceinline__ void tmem_load_cols(uint32_t taddr, uint32_t (&r)[16]) { tmem_load_32x16(taddr, r); }
+
 __device__ __forceinline__ void named_sync_softmax() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ============================================================================================= phase A
 constexpr int ST_KEYS = 128;
 constexpr int ST_STAGES = 4;
 constexpr int ST_TILE = ST_KEYS * 64 * 2;  // 16 KB
-constexpr int ST_OFF_X = QROWS * 128 + ST_STAGES * ST_TILE;  // (m2, l) exchange between the two column halves
-constexpr int ST_SMEM = ST_OFF_X + QROWS * 8 + 256 + 1024;
+constexpr int ST_PARTS = 4;                   // softmax warps per TMEM lane quarter (column parts of a 64-wide image row)
+constexpr int ST_PW = 64 / ST_PARTS;          // columns per part
+constexpr int kStThreads = 64 + ST_PARTS * 128;
+constexpr int ST_OFF_X = QROWS * 128 + ST_STAGES * ST_TILE;  // (m2, l) exchange between the column parts
+constexpr int ST_SMEM = ST_OFF_X + (ST_PARTS - 1) * QROWS * 8 + 256 + 1024;
 
 template <bool BF16>
-__global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const TcArgs a) {
+__global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const TcArgs a) {
     et_pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Qs = smem;
     uint8_t* Ks = smem + QROWS * 128;
     float2* xchg = reinterpret_cast<float2*>(smem + ST_OFF_X);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST_OFF_X + QROWS * 8);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST_OFF_X + (ST_PARTS - 1) * QROWS * 8);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;
     uint64_t* k_empty = k_full + ST_STAGES;
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
-            mbar_init(smem_u32(&s_empty[s]), 8);
+            mbar_init(smem_u32(&s_empty[s]), ST_PARTS * 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -177,18 +183,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
             PF_FLUSH(5);
         }
     } else {
+        // ST_PARTS softmax warps per TMEM lane quarter: warp (quarter, part) owns key columns [ST_PW part, +ST_PW) of
+        // each 64-wide image row.  Four parts = four softmax warps per scheduler: the exp2 / sum chains are latency-bound
+        // with two (profiles/r1_tc_stats_roles.txt).
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;  // key columns [32 half, 32 half + 32) of each 64-wide image row
+        const int part = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const size_t grow = ((size_t)b * a.H + h) * a.N + q0 + row;
         // rel-pos bias of this query row (stored as 8 x bias), in the log2 domain
         const float bscale = 0.125f * kLog2e;
-        float bwl[32];
+        float bwl[ST_PW];
         const uint16_t* bh_row = nullptr;
         if (a.has_bias) {
-            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.bias_w) + grow * 64 + half * 32);
+            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.bias_w) + grow * 64 + part * ST_PW);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < ST_PW / 8; ++c) {
                 const uint4 u4 = src[c];
                 const uint32_t w[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
             bh_row = static_cast<const uint16_t*>(a.bias_h) + grow * 64;
         } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) bwl[i] = 0.f;
+            for (int i = 0; i < ST_PW; ++i) bwl[i] = 0.f;
         }
         float m2 = -1e30f, l = 0.f;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -217,9 +226,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
             mbar_wait(smem_u32(&s_full[u]), (t >> 1) & 1);
             PF(0);
             tcgen05_fence_after();
-            uint32_t v0[32], v1[32];
-            tmem_load_32x32(taddr + (uint32_t)(u * ST_KEYS + half * 32), v0);       // image row 2t
-            tmem_load_32x32(taddr + (uint32_t)(u * ST_KEYS + 64 + half * 32), v1);  // image row 2t + 1
+            uint32_t v0[ST_PW], v1[ST_PW];
+            tmem_load_cols(taddr + (uint32_t)(u * ST_KEYS + part * ST_PW), v0);       // image row 2t
+            tmem_load_cols(taddr + (uint32_t)(u * ST_KEYS + 64 + part * ST_PW), v1);  // image row 2t + 1
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_empty[u]));
@@ -228,10 +237,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
             for (int c = 0; c < 2; ++c) {
                 const uint32_t* v = c ? v1 : v0;
                 const float bh = bh2[c];
-                float x[32];
+                float x[ST_PW];
                 float cmax = -1e30f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < ST_PW; ++i) {
                     x[i] = fmaf(__uint_as_float(v[i]), a.c1, bwl[i]);
                     cmax = fmaxf(cmax, x[i]);
                 }
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
                 const float shift = bh - m2;
                 float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
+                for (int i = 0; i < ST_PW; i += 2) {
                     sum0 += ex2_approx(x[i] + shift);
                     sum1 += ex2_approx(x[i + 1] + shift);
                 }
@@ -254,13 +263,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stats_kernel(const __grid_cons
         }
         PF(3);
         if (lane == 0 && warp == 2) PF_FLUSH(6);
-        // merge the two column halves of each row
-        if (half == 1) xchg[row] = make_float2(m2, l);
-        named_sync_softmax();
-        if (half == 0) {
-            const float2 o = xchg[row];
-            const float mm = fmaxf(m2, o.x);
-            l = l * ex2_approx(m2 - mm) + o.y * ex2_approx(o.x - mm);
+        // merge the column parts of each row
+        if (part > 0) xchg[(part - 1) * QROWS + row] = make_float2(m2, l);
+        asm volatile("bar.sync 1, %0;" ::"n"(ST_PARTS * 128) : "memory");
+        if (part == 0) {
+            float mm = m2;
+#pragma unroll
+            for (int o = 0; o < ST_PARTS - 1; ++o) mm = fmaxf(mm, xchg[o * QROWS + row].x);
+            l *= ex2_approx(m2 - mm);
+#pragma unroll
+            for (int o = 0; o < ST_PARTS - 1; ++o) {
+                const float2 ov = xchg[o * QROWS + row];
+                l += ov.y * ex2_approx(ov.x - mm);
+            }
             a.stats[grow * 2] = mm;
             a.stats[grow * 2 + 1] = l;
         }
@@ -714,7 +729,7 @@ int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, i
         ET_COUNT_LAUNCH(1);
     }
     const dim3 grid(a.N / QROWS, a.H, a.B);
-    et_launch(tc_stats_kernel<BF16>, dim3(grid), dim3(kThreads), ST_SMEM, s, tm128, a);
+    et_launch(tc_stats_kernel<BF16>, dim3(grid), dim3(kStThreads), ST_SMEM, s, tm128, a);
     ET_COUNT_LAUNCH(1);
     if (g_tc_time_apply) {
         if (g_ev0 == nullptr) {
