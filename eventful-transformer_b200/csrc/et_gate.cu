@@ -13,6 +13,7 @@
 
 thread_local char g_et_error[512] = "";
 long long g_et_launches = 0;
+int g_gate_cta_waves = 2;  // CTAs of the gate kernels per SM over the whole launch (et_debug_set key 10)
 int g_et_pdl = []() { const char* e = getenv("EVENTFUL_B200_PDL"); return (e && e[0] == '1') ? 1 : 0; }();
 
 unsigned long long* g_gate_dbg = nullptr;  // et_debug_set(3, device pointer to 8 x u64) enables phase timestamps
@@ -696,7 +697,7 @@ int et_gate_select(const void* xa, const void* xb, void* xsum_out, const void* l
         const int lpt = nchunks <= 1 ? 1 : nchunks <= 2 ? 2 : nchunks <= 4 ? 4 : nchunks <= 8 ? 8 : nchunks <= 16 ? 16 : 32;
         const int groups = kGateThreads / lpt;
         // ~4 CTAs per SM over the whole launch (all resident: more loads in flight), each CTA at least one pass
-        long long want = (2 * 148 + R - 1) / R;
+        long long want = (g_gate_cta_waves * 148 + R - 1) / R;
         long long max_ctas = (N + groups - 1) / groups;
         long long ctas = want < 1 ? 1 : (want > max_ctas ? max_ctas : want);
         a.tokens_per_cta = (int)((N + ctas - 1) / ctas);

@@ -603,6 +603,7 @@ extern int g_attn_tc;
 extern unsigned long long* g_gate_dbg;
 extern int g_tc_time_apply;
 extern unsigned long long* g_tc_prof;
+extern int g_gate_cta_waves;
 
 extern "C" {
 
@@ -625,6 +626,10 @@ int et_debug_set(int key, long long value) {
     }
     if (key == 9) {
         g_force_persist = (int)value;
+        return ET_OK;
+    }
+    if (key == 10) {
+        g_gate_cta_waves = value > 0 ? (int)value : 2;
         return ET_OK;
     }
     if (key == 2) {

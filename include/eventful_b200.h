@@ -101,7 +101,7 @@ int et_sub(const void* a, const void* b, void* out, int64_t n, int dtype, void* 
  * 2 shallow = two CTAs per SM, 0 = automatic); key 6: 1 brackets the global-attention apply kernel with CUDA events;
  * key 4 / key 7: device pointer to 8 x 16 / 3 x 16 uint64 cycle buckets per warp role of the attention / GEMM kernels
  * (written only by the profiling build, `make prof`); key 8: GEMM rows per CTA tile (1 = 128, 2 = 256, 0 = automatic);
- * key 9: persistent GEMM kernel (1 = always, 2 = never, 0 = automatic). */
+ * key 9: persistent GEMM kernel (1 = always, 2 = never, 0 = automatic); key 10: CTAs per SM of the gate kernels (default 2). */
 int et_debug_set(int key, long long value);
 /* Milliseconds of the last apply-kernel launch bracketed under key 6 (synchronises on its end event). */
 float et_debug_elapsed_ms(void);
