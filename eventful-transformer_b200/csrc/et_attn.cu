@@ -250,7 +250,9 @@ __global__ void __launch_bounds__(kAttnThreads) relpos_bias_kernel(const AttnArg
 // ---------------------------------------------------------------- rel-pos bias, windowed blocks, one CTA per (window, head)
 // Stages the window's q rows and both relative tables in shared memory once, then each warp walks lines
 // (all tokens sharing ly, or sharing lx): a 16 x 16 x DH product per line with ldmatrix row gathers.
-// Output: combined tensor-core layout (Bw, H, 256, 64): columns [0, wh) = 8 bias_h, [wh, wh + ww) = 8 bias_w.
+// Output: compact tensor-core layout (Bw, H, 256, 32): columns [0, wh) = 8 bias_h, [wh, wh + ww) = 8 bias_w, zeros
+// elsewhere (wh + ww <= 32).  The tile is assembled in shared memory and written as one contiguous 16 KB block, so the
+// scratch needs no memset and the attention kernel reads 64 bytes per query row.
 template <typename T, int DH>
 __global__ void __launch_bounds__(kAttnThreads) relpos_window_kernel(const AttnArgs a, const T* rel_y, const T* rel_x, T* comb,
                                                                       float scale) {
@@ -261,6 +263,9 @@ __global__ void __launch_bounds__(kAttnThreads) relpos_window_kernel(const AttnA
     T* Qs = reinterpret_cast<T*>(smraw);            // [Wn + 1][LD], last row = zeros
     T* Ty = Qs + (Wn + 1) * LD;                     // [wh * wh + 1][LD]
     T* Tx = Ty + (wh * wh + 1) * LD;                // [ww * ww + 1][LD]
+    T* Cs = Tx + (ww * ww + 1) * LD;                // [256][32] output tile
+    for (int c = threadIdx.x; c < 256 * 32 * (int)sizeof(T) / 16; c += kAttnThreads)
+        reinterpret_cast<uint4*>(Cs)[c] = make_uint4(0, 0, 0, 0);
     const TokenMap map = make_map(a);
     const int bw = blockIdx.x, h = blockIdx.y;
     const int nwin = a.nwx * a.nwy;
@@ -278,7 +283,6 @@ __global__ void __launch_bounds__(kAttnThreads) relpos_window_kernel(const AttnA
     stage_rows<T, DH, LD>(Tx, ww * ww + 1, [&](int r) -> const T* { return r < ww * ww ? rel_x + (size_t)r * DH : nullptr; });
     cp_async_wait_all();
     __syncthreads();
-    T* dst = comb + ((size_t)bw * a.H + h) * 256 * 64;
     for (int line = warp; line < wh + ww; line += kAttnThreads / 32) {
         const bool ymode = line < wh;
         const int fixed = ymode ? line : line - wh;
@@ -307,12 +311,15 @@ __global__ void __launch_bounds__(kAttnThreads) relpos_window_kernel(const AttnA
                         const int kc = o0 + nt * 8 + tq * 2 + (i & 1);
                         if (j < ntok && kc < nout) {
                             const int t = ymode ? fixed * ww + j : j * ww + fixed;
-                            dst[(size_t)t * 64 + (ymode ? 0 : wh) + kc] = ElemTraits<T>::from_float(acc[nt][i] * scale);
+                            Cs[t * 32 + (ymode ? 0 : wh) + kc] = ElemTraits<T>::from_float(acc[nt][i] * scale);
                         }
                     }
             }
         }
     }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(comb + ((size_t)bw * a.H + h) * 256 * 32);
+    for (int c = threadIdx.x; c < 256 * 32 * (int)sizeof(T) / 16; c += kAttnThreads) dst[c] = reinterpret_cast<const uint4*>(Cs)[c];
 }
 
 // ---------------------------------------------------------------- windowed / small dense attention
@@ -793,12 +800,10 @@ int run_window(const AttnArgs& a, const void* rel_y, const void* rel_x, void* bi
     const int nwin = a.windowed ? a.nwx * a.nwy : 1;
     AttnArgs args = a;
     // tensor-core path: real windows of at most 208 tokens, dh = 64, rel-pos coordinates fitting one 64-column block
-    if (a.windowed && DH == 64 && a.Wn <= 208 && (rel_y == nullptr || lh + lw <= 64) && g_attn_tc) {
+    if (a.windowed && DH == 64 && a.Wn <= 208 && (rel_y == nullptr || lh + lw <= 32) && g_attn_tc) {
         if (rel_y != nullptr) {
             T* comb = static_cast<T*>(bias_ws);
-            const size_t bytes = (size_t)a.B * nwin * a.H * 256 * 64 * sizeof(T);
-            if (cudaMemsetAsync(comb, 0, bytes, s) != cudaSuccess) return et_fail(ET_ERR_CUDA, "cudaMemsetAsync failed");
-            const int smem_rp = ((a.Wn + 1) + (lh * lh + 1) + (lw * lw + 1)) * (DH + 8) * (int)sizeof(T) + 16;
+            const int smem_rp = ((a.Wn + 1) + (lh * lh + 1) + (lw * lw + 1)) * (DH + 8) * (int)sizeof(T) + 256 * 32 * (int)sizeof(T) + 16;
             int rc = set_smem(relpos_window_kernel<T, DH>, smem_rp);
             if (rc) return rc;
             et_launch(relpos_window_kernel<T, DH>, dim3(dim3(a.B * nwin, a.H)), dim3(kAttnThreads), smem_rp, s, a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), comb, 8.f);

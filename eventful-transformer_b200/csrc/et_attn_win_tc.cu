@@ -6,7 +6,9 @@
 //     (B, gh, gw, 3D) token grid in window-local order; out-of-grid rows arrive as zeros and are patched to the
 //     qkv bias vector (the image of a zero token, blocks.py:275-287);
 //   * S' = Q' K'^T with Q' = [q | 8 bias_h | 8 bias_w | 0], K' = [k | onehot(ly) | onehot(lx) | 0]: the decomposed
-//     rel-pos bias comes out of the MMA; M = 2 x 128 query rows (w^2 <= 256), N = w^2 rounded up to 16 keys;
+//     rel-pos bias comes out of the MMA; M = 2 x 128 query rows (w^2 <= 256), N = w^2 rounded up to 16 keys.  The
+//     bias part is 32 columns wide (wh + ww <= 32): 64 bytes per query row, fetched with cp.async into the swizzled
+//     operand rows, and two K = 16 MMAs;
 //   * two softmax warpgroups (one per 128-row half, one row per thread) take max / exp2 / sum straight from TMEM and
 //     write P as an MN-major A tile that overlays the (now dead) Q' / K' operand memory;
 //   * O = P V with V as MN-major B operand from TMA; epilogue scales by 1 / l and writes only in-grid rows.
@@ -32,6 +34,7 @@ static_assert(4 * W_PBLK <= W_OFF_V, "P tiles must fit inside the Q'/K' operand 
 
 struct WinArgs {
     const void* pad_token;  // qkv bias (3D)
+    const void* bias;       // (B * nwin * H, 256, 32): [8 bias_h | 8 bias_w | 0] per window-local query row
     void* out;
     int B, N, gh, gw, wh, ww, nwx, nwy, H, D, Wn, NK, has_bias, is_bf16;
     float c1;
@@ -105,14 +108,11 @@ tc_window_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         if (lane == 0) {
             const uint32_t fb = smem_u32(ld_full);
             const int rows = a.Wn * 128;
-            mbar_expect_tx(fb, 3 * rows + (a.has_bias ? 2 * 128 * 128 + a.NK * 128 : 0));
+            mbar_expect_tx(fb, 3 * rows + (a.has_bias ? a.NK * 128 : 0));
             tma_load_4d(smem_u32(Qq), &tm_qkv, fb, h * 64, wx * a.ww, wy * a.wh, b);
             tma_load_4d(smem_u32(Kk), &tm_qkv, fb, a.D + h * 64, wx * a.ww, wy * a.wh, b);
             tma_load_4d(smem_u32(Vs), &tm_qkv, fb, 2 * a.D + h * 64, wx * a.ww, wy * a.wh, b);
             if (a.has_bias) {
-                const int brow = (bw * a.H + h) * 256;
-                tma_load_2d(smem_u32(Qb), &tm_bias, fb, 0, brow);
-                tma_load_2d(smem_u32(Qb + 128 * 128), &tm_bias, fb, 0, brow + 128);
                 tma_load_2d(smem_u32(Koh), &tm_oh, fb, 0, 0);
             }
         }
@@ -126,8 +126,8 @@ tc_window_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
                 for (int kb = 0; kb < nkb; ++kb) {
                     const uint64_t dq = umma_smem_desc(smem_u32((kb ? Qb : Qq) + m * 128 * 128));
                     const uint64_t dk = umma_smem_desc(smem_u32(kb ? Koh : Kk));
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
+                    const int nkk = kb ? 2 : 4;  // the bias / one-hot block carries 32 meaningful columns
+                    for (int kk = 0; kk < nkk; ++kk)
                         tcgen05_mma_f16(tmem_base + m * 256, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s,
                                         (kb > 0 || kk > 0));
                 }
@@ -153,6 +153,13 @@ tc_window_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         const int row = quarter * 32 + lane;      // row inside the half
         const int wrow = m * 128 + row;           // window-local token
         const uint16_t* pad = static_cast<const uint16_t*>(a.pad_token);
+        // ---- this thread's bias row: 64 bytes (8 bias_h | 8 bias_w | 0) -> logical chunks 0-3 of the swizzled operand row
+        if (a.has_bias) {
+            const uint16_t* brow = static_cast<const uint16_t*>(a.bias) + ((size_t)(bw * a.H + h) * 256 + st) * 32;
+            uint8_t* qrow = Qb + st * 128;  // rows 128-255 continue in the second 16 KB block
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cp_async_16(smem_u32(qrow + ((c ^ (st & 7)) << 4)), brow + c * 8);
+        }
         // ---- rows that TMA does not write must be finite: zero rows [Wn, 256) of Q and [Wn, NK) of K / V
         for (int c = st; c < (256 - a.Wn) * 8; c += 256)
             *reinterpret_cast<uint4*>(Qq + (a.Wn + c / 8) * 128 + (c & 7) * 16) = make_uint4(0, 0, 0, 0);
@@ -174,6 +181,7 @@ tc_window_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
                 }
             }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(ops_ready));
@@ -302,14 +310,14 @@ int make_tmap_grid4d(CUtensorMap* map, const void* base, int B, int gh, int gw, 
 
 }  // namespace
 
-// Bytes of bias scratch: (B * nwin * H, 256, 64) combined [8 bias_h | 8 bias_w | 0] rows + the (256, 64) one-hot block.
-long long et_tc_window_scratch_elems(int B, int nwin, int H) { return (long long)B * nwin * H * 256 * 64 + 256 * 64; }
+// Elements of bias scratch: (B * nwin * H, 256, 32) combined [8 bias_h | 8 bias_w | 0] rows + the (256, 64) one-hot block.
+long long et_tc_window_scratch_elems(int B, int nwin, int H) { return (long long)B * nwin * H * 256 * 32 + 256 * 64; }
 
 // bias_comb: scratch as above, already filled by relpos_bias_kernel in the combined window layout (or nullptr).
 int et_tc_window_attention(const void* qkv, const void* pad_token, void* bias_comb, void* out, int B, int N, int gh, int gw,
                            int wh, int ww, int H, int has_bias, int is_bf16, cudaStream_t s) {
     WinArgs a;
-    a.pad_token = pad_token; a.out = out; a.B = B; a.N = N; a.gh = gh; a.gw = gw; a.wh = wh; a.ww = ww;
+    a.pad_token = pad_token; a.bias = bias_comb; a.out = out; a.B = B; a.N = N; a.gh = gh; a.gw = gw; a.wh = wh; a.ww = ww;
     a.nwy = (gh + wh - 1) / wh; a.nwx = (gw + ww - 1) / ww; a.H = H; a.D = H * 64; a.Wn = wh * ww;
     a.NK = (a.Wn + 15) / 16 * 16; a.has_bias = has_bias; a.is_bf16 = is_bf16; a.c1 = 0.125f * kLog2e;
     const int nwin = a.nwx * a.nwy;
@@ -325,8 +333,7 @@ int et_tc_window_attention(const void* qkv, const void* pad_token, void* bias_co
     if ((rc = make_tmap_grid4d(&tq, qkv, B, gh, gw, 3 * a.D, wh, ww, is_bf16))) return rc;
     tb = toh = tq;
     if (has_bias) {
-        uint16_t* oh = static_cast<uint16_t*>(bias_comb) + (size_t)B * nwin * H * 256 * 64;
-        if ((rc = make_tmap_2d(&tb, bias_comb, (long long)B * nwin * H * 256, 64, 128, is_bf16))) return rc;
+        uint16_t* oh = static_cast<uint16_t*>(bias_comb) + (size_t)B * nwin * H * 256 * 32;
         if ((rc = make_tmap_2d(&toh, oh, 256, 64, a.NK, is_bf16))) return rc;
         if (is_bf16) et_launch(window_onehot_kernel<true>, dim3(8), dim3(256), 0, s, oh, wh, ww);
         else et_launch(window_onehot_kernel<false>, dim3(8), dim3(256), 0, s, oh, wh, ww);
