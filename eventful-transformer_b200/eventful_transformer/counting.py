@@ -1,133 +1,135 @@
 """
-Counted operators: they own the parameters (state-dict keys `weight`, `bias`) and the MAC
-counters, and run on libeventful_b200.  API mirror of the reference's counting.py.
+Operators that own parameters (state-dict keys `weight`, `bias`) and MAC counters, executed by
+libeventful_b200.  Same class names, constructor arguments and counter keys as the reference's
+counting.py, so its models build on top of this module unchanged.
 
-Counter semantics (MACs, not FLOPs) follow counting.py:16-19,43-47,98-110,119-124,146-162,171-175.
-Parameters are zero-initialised like the reference's (counting.py:143-144): callers load or
-initialise weights explicitly.
+What is counted (multiply-accumulates, not FLOPs; reference counting.py:16-19,43-47,98-110,119-124,
+146-162,171-175):
+    add_flops / bias_flops   one per output element
+    linear_flops             rows x in_features x out_features
+    matmul_flops             output elements x inner dimension
+    conv{n}d_flops           output elements x (in_channels / groups) x prod(kernel)
+    einsum_flops             the einsum of all-ones operands
+Parameters start at zero, as in the reference (counting.py:143-144): weights are loaded or initialised by
+the caller.
 """
 
 from math import prod
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from eventful_transformer import _native as native
 from eventful_transformer.base import ExtendedModule, numeric_tuple
 
 
-class CountedAdd(ExtendedModule):
-    """result = a + b (optionally in place on a); counts result.numel() adds."""
+class _Counted(ExtendedModule):
+    def _tally(self, key, macs):
+        if self.count_mode:
+            self.counts[key] += int(macs)
+
+
+def _zeros_parameter(shape, device, dtype):
+    return nn.Parameter(torch.zeros(shape, device=device, dtype=dtype))
+
+
+class CountedAdd(_Counted):
+    """Elementwise sum (residual connections, position encoding); `inplace` reuses the first operand."""
 
     def forward(self, a, b, inplace=False):
-        if a.shape != b.shape:
-            b = b.expand_as(a).contiguous()  # broadcast operand materialised once (e.g. position encoding)
-        result = native.add(a, b, out=a if inplace else None)
-        if self.count_mode:
-            self.counts["add_flops"] += result.numel()
-        return result
+        rhs = b if b.shape == a.shape else b.expand_as(a).contiguous()  # e.g. a (1, N, D) position encoding
+        total = native.add(a, rhs, out=a if inplace else None)
+        self._tally("add_flops", total.numel())
+        return total
 
 
-class CountedBias(ExtendedModule):
-    """x + bias over a channel dimension followed by `spatial_dims` trailing dims."""
+class CountedBias(_Counted):
+    """Adds a per-channel bias; the channel axis is followed by `spatial_dims` trailing axes."""
 
     def __init__(self, features, spatial_dims=0, device=None, dtype=None):
         super().__init__()
-        self.features = features
-        self.spatial_dims = spatial_dims
-        self.bias = nn.Parameter(torch.zeros(features, device=device, dtype=dtype))
+        self.features, self.spatial_dims = features, spatial_dims
+        self.bias = _zeros_parameter(features, device, dtype)
 
     def forward(self, x):
-        bias = self.bias.view((self.features,) + (1,) * self.spatial_dims).expand_as(x).contiguous()
-        result = native.add(x.contiguous(), bias)
-        if self.count_mode:
-            self.counts["bias_flops"] += result.numel()
-        return result
+        shaped = self.bias.view((self.features,) + (1,) * self.spatial_dims)
+        total = native.add(x.contiguous(), shaped.expand_as(x).contiguous())
+        self._tally("bias_flops", total.numel())
+        return total
 
 
-class CountedConv(ExtendedModule):
+class CountedConv(_Counted):
     """
-    Convolution used by the patch / tubelet embeddings in models/ (outside the gated path,
-    SURVEY.md 8(f4)).  Keeps the reference's parameter layout and counter; the convolution
-    itself is delegated to the cuDNN library call, as a plain library op off the hot path.
+    N-d convolution of the patch / tubelet embeddings in models/ (outside the gated path).
+    Parameter layout and counter follow the reference; the convolution itself is the cuDNN library op.
     """
 
     def __init__(self, spatial_dims, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
                  groups=1, device=None, dtype=None):
         super().__init__()
-        self.spatial_dims = spatial_dims
-        self.in_channels = in_channels
-        self.out_channels = out_channels
-        self.kernel_size = numeric_tuple(kernel_size, length=spatial_dims)
-        self.stride = numeric_tuple(stride, length=spatial_dims)
-        self.padding = numeric_tuple(padding, length=spatial_dims) if isinstance(padding, int) else padding
-        self.dilation = numeric_tuple(dilation, length=spatial_dims)
-        self.groups = groups
-        self.conv_function = getattr(torch.nn.functional, f"conv{spatial_dims}d")
-        shape = (out_channels, in_channels // groups) + self.kernel_size
-        self.weight = nn.Parameter(torch.zeros(shape, device=device, dtype=dtype))
+        per_axis = lambda value: numeric_tuple(value, length=spatial_dims)  # noqa: E731
+        self.spatial_dims, self.groups = spatial_dims, groups
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.dilation = per_axis(kernel_size), per_axis(stride), per_axis(dilation)
+        self.padding = per_axis(padding) if isinstance(padding, int) else padding  # strings such as "same" pass through
+        self.conv_function = getattr(F, f"conv{spatial_dims}d")
+        self.weight = _zeros_parameter((out_channels, in_channels // groups) + self.kernel_size, device, dtype)
 
     def forward(self, x):
-        result = self.conv_function(x, self.weight, stride=self.stride, padding=self.padding,
-                                    dilation=self.dilation, groups=self.groups)
-        if self.count_mode:
-            fan_in = (self.in_channels // self.groups) * prod(self.kernel_size)
-            self.counts[f"conv{self.spatial_dims}d_flops"] += result.numel() * fan_in
-        return result
+        y = self.conv_function(x, self.weight, None, self.stride, self.padding, self.dilation, self.groups)
+        self._tally(f"conv{self.spatial_dims}d_flops", y.numel() * (self.in_channels // self.groups) * prod(self.kernel_size))
+        return y
 
 
-class CountedEinsum(ExtendedModule):
+class CountedEinsum(_Counted):
     """
-    Einsum with a MAC counter.  Only the rel-pos einsums sit on the gated path and those are fused into
-    the attention kernels; this generic operator remains for API compatibility (library call).
+    Generic einsum with a MAC counter, kept for API compatibility (library call).  The rel-pos einsums of the
+    gated path never come here: they are fused into the attention kernels.
     """
 
     def forward(self, equation, *operands):
         if self.count_mode:
-            ones = [torch.ones_like(x) for x in operands]
-            self.counts["einsum_flops"] += int(torch.einsum(equation, *ones).sum())
+            self._tally("einsum_flops", torch.einsum(equation, *[torch.ones_like(op) for op in operands]).sum())
         return torch.einsum(equation, *operands)
 
 
-class CountedLinear(ExtendedModule):
-    """y = x W^T + b on the tcgen05 GEMM; weight (out, in), bias (out)."""
+class CountedLinear(_Counted):
+    """Affine layer on the tcgen05 GEMM: weight (out_features, in_features), bias (out_features)."""
 
     def __init__(self, in_features, out_features, device=None, dtype=None):
         super().__init__()
-        self.in_features = in_features
-        self.out_features = out_features
-        self.weight = nn.Parameter(torch.zeros((out_features, in_features), device=device, dtype=dtype))
-        self.bias = nn.Parameter(torch.zeros(out_features, device=device, dtype=dtype))
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = _zeros_parameter((out_features, in_features), device, dtype)
+        self.bias = _zeros_parameter(out_features, device, dtype)
 
     def count_linear(self, n_rows, with_bias=True):
-        """Adds the counters of a linear applied to n_rows input rows (used by the fused block path)."""
-        if self.count_mode:
-            if with_bias:
-                self.counts["bias_flops"] += n_rows * self.out_features
-            self.counts["linear_flops"] += n_rows * self.in_features * self.out_features
-
-    def forward_bias(self, x):
-        result = native.add(x.contiguous(), self.bias.detach().expand_as(x).contiguous())
-        if self.count_mode:
-            self.counts["bias_flops"] += result.numel()
-        return result
-
-    def forward_linear(self, x):
-        if self.count_mode:
-            self.counts["linear_flops"] += x.numel() * self.out_features
-        return native.linear(x.contiguous(), self.weight.detach(), None)
+        """Counters of this layer applied to n_rows rows (the fused block path calls the GEMM directly)."""
+        if with_bias:
+            self._tally("bias_flops", n_rows * self.out_features)
+        self._tally("linear_flops", n_rows * self.in_features * self.out_features)
 
     def forward(self, x, act=native.ACT_NONE, out=None, idx=None):
-        result = native.linear(x.contiguous(), self.weight.detach(), self.bias.detach(), act=act, out=out, idx=idx)
+        y = native.linear(x.contiguous(), self.weight.detach(), self.bias.detach(), act=act, out=out, idx=idx)
         self.count_linear(x.numel() // self.in_features)
-        return result
+        return y
+
+    def forward_linear(self, x):
+        """The product alone (reference counting.py:157-158)."""
+        self.count_linear(x.numel() // self.in_features, with_bias=False)
+        return native.linear(x.contiguous(), self.weight.detach(), None)
+
+    def forward_bias(self, x):
+        """The bias alone: what a zero token maps to, used for window padding (reference counting.py:152-155)."""
+        y = native.add(x.contiguous(), self.bias.detach().expand_as(x).contiguous())
+        self._tally("bias_flops", y.numel())
+        return y
 
 
-class CountedMatmul(ExtendedModule):
-    """Batched a @ b with a MAC counter (strided operands accepted)."""
+class CountedMatmul(_Counted):
+    """Batched matrix product with a MAC counter; strided operands are accepted."""
 
     def forward(self, a, b):
-        result = native.bmm(a, b)
-        if self.count_mode:
-            self.counts["matmul_flops"] += result.numel() * a.shape[-1]
-        return result
+        y = native.bmm(a, b)
+        self._tally("matmul_flops", y.numel() * a.shape[-1])
+        return y

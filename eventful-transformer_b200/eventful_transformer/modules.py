@@ -32,198 +32,179 @@ def _broadcast_index(index, target):
     return view.expand(lead + (index.shape[-1],)).contiguous()
 
 
-class _GateBase(ExtendedModule):
-    def __init__(self, structure="row"):
+class _FrameState(ExtendedModule):
+    """
+    Shared skeleton of every gating primitive: `first` tells frame 0 from the incremental frames and
+    `_state` names the attributes that hold the per-stream tensors.  reset_self() (called by
+    ExtendedModule.reset, base.py) drops them, so the next call is a first frame again.
+    """
+
+    _state = ()
+
+    def __init__(self):
         super().__init__()
-        assert structure in ["row", "col"]
-        self.structure = structure
+        self._drop_state()
+
+    def _drop_state(self):
         self.first = True
-        self.policy = None
-        self.p = None
+        for name in self._state:
+            setattr(self, name, None)
 
     def reset_self(self):
-        self.first = True
-        self.p = None
+        self._drop_state()
 
+    def _tally(self, key, amount):
+        if self.count_mode:
+            self.counts[key] += amount
+
+
+class _GateBase(_FrameState):
+    """
+    Row / column gate against a reference tensor p (modules.py:104-201).  `_with_delta` selects the
+    TokenDeltaGate flavour, whose results carry the gathered error e~ as well.
+    """
+
+    _state = ("p",)
+    _with_delta = False
+
+    def __init__(self, structure="row"):
+        assert structure in ("row", "col")
+        super().__init__()
+        self.structure = structure
+        self.policy = None
+
+    # -- selection and state advance through the gate kernels
     def _select(self, c, p):
-        """Index chosen by self.policy for gate input c against state p."""
-        if self.structure == "row":
-            spec = _policy_spec(self.policy, c.shape[-2])
-            if spec is not None:
-                if "threshold" in spec:
-                    assert all(size == 1 for size in c.shape[:-2])  # policies.py:25
-                index, _ = native.gate_select(c, p=p, **spec)
-                return index
-            return self.policy(native.sub(c, p), dim=-1)
-        return self.policy(native.sub(c, p), dim=-2)
+        along_rows = self.structure == "row"
+        spec = _policy_spec(self.policy, c.shape[-2]) if along_rows else None
+        if spec is None:  # user-defined policy (or column structure): materialise the error tensor
+            return self.policy(native.sub(c, p), dim=-1 if along_rows else -2)
+        if "threshold" in spec:
+            assert all(size == 1 for size in c.shape[:-2])  # policies.py:25
+        return native.gate_select(c, p=p, **spec)[0]
 
-    def _update(self, c, index, want_delta):
-        """c~ (and e~) at index, and p[index] = c~."""
+    def _update(self, c, index):
         if self.structure == "row":
-            return native.gate_gather(c, _broadcast_index(index, c), p=self.p, want_delta=want_delta)
-        return native.gate_gather_cols(c, index.contiguous(), p=self.p, want_delta=want_delta)
+            return native.gate_gather(c, _broadcast_index(index, c), p=self.p, want_delta=self._with_delta)
+        return native.gate_gather_cols(c, index.contiguous(), p=self.p, want_delta=self._with_delta)
+
+    def _pack(self, c_tilde, e_tilde, index):
+        return (c_tilde, e_tilde, index) if self._with_delta else (c_tilde, index)
+
+    # -- public protocol of the reference
+    def forward(self, c, forced_index=None):
+        """Note: p aliases the first input ever seen and is advanced in place afterwards."""
+        return self.forward_first(c) if self.first else self.forward_incremental(c, forced_index=forced_index)
+
+    def forward_first(self, c):
+        self.first, self.p = False, c
+        return self._pack(c, None, None)
+
+    def forward_incremental(self, c, forced_index=None):
+        self._tally("gate_flops", self.p.numel())
+        c = c.contiguous()
+        index = forced_index if forced_index is not None else self._select(c, self.p)
+        c_tilde, e_tilde = self._update(c, index)
+        return self._pack(c_tilde, e_tilde, index)
 
 
 class TokenGate(_GateBase):
-    """Token gate: selects tokens whose value drifted from the reference state p (modules.py:104-168)."""
-
-    def forward(self, c, forced_index=None):
-        """Warning - self.p keeps a direct reference to the first input and is updated in place."""
-        if self.first:
-            return self.forward_first(c)
-        return self.forward_incremental(c, forced_index=forced_index)
-
-    def forward_first(self, c):
-        self.first = False
-        self.p = c
-        return c, None
-
-    def forward_incremental(self, c, forced_index=None):
-        if self.count_mode:
-            self.counts["gate_flops"] += self.p.numel()
-        c = c.contiguous()
-        index = self._select(c, self.p) if forced_index is None else forced_index
-        c_tilde, _ = self._update(c, index, want_delta=False)
-        return c_tilde, index
+    """Selects the tokens whose value drifted from the reference state p; returns (c~, index)."""
 
 
 class TokenDeltaGate(_GateBase):
-    """Token gate that also returns the gathered error e~ (modules.py:171-201)."""
+    """TokenGate that also returns the gathered error: (c~, e~, index) (modules.py:171-201)."""
 
-    def forward(self, c, forced_index=None):
-        if self.first:
-            return self.forward_first(c)
-        return self.forward_incremental(c, forced_index=forced_index)
-
-    def forward_first(self, c):
-        self.first = False
-        self.p = c
-        return c, None, None
-
-    def forward_incremental(self, c, forced_index=None):
-        if self.count_mode:
-            self.counts["gate_flops"] += self.p.numel()
-        c = c.contiguous()
-        index = self._select(c, self.p) if forced_index is None else forced_index
-        c_tilde, e_tilde = self._update(c, index, want_delta=True)
-        return c_tilde, e_tilde, index
+    _with_delta = True
 
 
-class SimpleSTGTGate(ExtendedModule):
-    """Baseline gate of "Spatio-Temporal Gated Transformers": p is replaced wholesale (modules.py:6-49)."""
+class SimpleSTGTGate(_FrameState):
+    """Baseline gate of "Spatio-Temporal Gated Transformers": p is replaced wholesale each frame (modules.py:6-49)."""
+
+    _state = ("p",)
 
     def __init__(self, structure="row"):
-        super().__init__()
         assert structure == "row"
-        self.first = True
+        super().__init__()
         self.policy = None
-        self.p = None
 
     def forward(self, c):
         if self.first:
-            self.first = False
-            self.p = c
+            self.first, self.p = False, c
             return c, None
-        if self.count_mode:
-            self.counts["gate_flops"] += c.numel()
+        self._tally("gate_flops", c.numel())
         c = c.contiguous()
         spec = _policy_spec(self.policy, c.shape[-2])
-        if spec is not None:
-            index, _ = native.gate_select(c, p=self.p, **spec)
-        else:
+        if spec is None:
             index = self.policy(native.sub(c, self.p), dim=-1)
-        c_tilde, _ = native.gate_gather(c, _broadcast_index(index, c))
+        else:
+            index = native.gate_select(c, p=self.p, **spec)[0]
         self.p = c
-        return c_tilde, index
-
-    def reset_self(self):
-        self.first = True
-        self.p = None
+        return native.gate_gather(c, _broadcast_index(index, c))[0], index
 
 
-class TokenBuffer(ExtendedModule):
-    """Token buffer: scatters updated tokens into a persistent tensor (modules.py:52-101)."""
+class TokenBuffer(_FrameState):
+    """Persistent tensor b into which updated rows / columns are scattered (modules.py:52-101); returns b itself."""
+
+    _state = ("b",)
 
     def __init__(self, structure="row"):
+        assert structure in ("row", "col")
         super().__init__()
-        assert structure in ["row", "col"]
         self.structure = structure
-        self.first = True
-        self.b = None
 
     def forward(self, x, index):
-        """Warning - the output is a direct reference to self.b."""
-        if self.first:
-            return self.forward_first(x)
-        return self.forward_incremental(x, index)
+        return self.forward_first(x) if self.first else self.forward_incremental(x, index)
 
     def forward_first(self, x):
-        self.first = False
-        self.b = x.clone()
+        self.first, self.b = False, x.clone()
         return self.b
 
     def forward_incremental(self, x, index):
         native.buffer_scatter(self.b, x.contiguous(), index.contiguous(), structure=self.structure)
         return self.b
 
-    def reset_self(self):
-        self.first = True
-        self.b = None
 
-
-class MatmulBuffer(ExtendedModule):
-    """
-    Query-key product buffer (modules.py:204-252): rows index_q then columns index_k are refreshed.
-    The Eventful blocks of this package do not keep this N x N state -- the product always equals
-    (q / scale) k^T of the current QKV buffer, so the attention kernels recompute it on tensor cores.
-    """
+class _ProductState(_FrameState):
+    _state = ("product",)
 
     def __init__(self):
         super().__init__()
-        self.first = True
-        self.product = None
         self.matmul = CountedMatmul()
 
-    def forward(self, q, k, index_q, index_k):
-        """Warning - the output is a direct reference to self.product."""
-        if self.first:
-            self.first = False
-            self.product = self.matmul(q, k)
-            return self.product
-        q_tilde, _ = native.gate_gather(q.contiguous(), _broadcast_index(index_q, q))
-        k_tilde, _ = native.gate_gather_cols(k.contiguous(), index_k.contiguous())
-        native.buffer_scatter(self.product, self.matmul(q_tilde, k), index_q.contiguous(), structure="row")
-        native.buffer_scatter(self.product, self.matmul(q, k_tilde), index_k.contiguous(), structure="col")
+    def _first_product(self, a, b):
+        self.first, self.product = False, self.matmul(a, b)
         return self.product
 
-    def reset_self(self):
-        self.first = True
-        self.product = None
+
+class MatmulBuffer(_ProductState):
+    """
+    Query-key product buffer (modules.py:204-252): rows index_q, then columns index_k are refreshed; the
+    result is the state tensor itself.  The Eventful blocks of this package do not keep this N x N state:
+    the product always equals (q / scale) k^T of the current QKV buffer, so the attention kernels recompute
+    it on tensor cores.
+    """
+
+    def forward(self, q, k, index_q, index_k):
+        if self.first:
+            return self._first_product(q, k)
+        rows = native.gate_gather(q.contiguous(), _broadcast_index(index_q, q))[0]
+        cols = native.gate_gather_cols(k.contiguous(), index_k.contiguous())[0]
+        native.buffer_scatter(self.product, self.matmul(rows, k), index_q.contiguous(), structure="row")
+        native.buffer_scatter(self.product, self.matmul(q, cols), index_k.contiguous(), structure="col")
+        return self.product
 
 
-class MatmulDeltaAccumulator(ExtendedModule):
-    """Attention-value product accumulator (modules.py:255-299)."""
-
-    def __init__(self):
-        super().__init__()
-        self.first = True
-        self.product = None
-        self.matmul = CountedMatmul()
+class MatmulDeltaAccumulator(_ProductState):
+    """Attention-value product updated by the two delta terms of modules.py:285-295; returns the state tensor."""
 
     def forward(self, a_n_tilde, v_n_tilde, a_delta_tilde, v_delta_tilde):
-        """Warning - the output is a direct reference to self.product."""
         if self.first:
-            self.first = False
-            self.product = self.matmul(a_n_tilde, v_n_tilde)
-            return self.product
+            return self._first_product(a_n_tilde, v_n_tilde)
         if self.count_mode:
             self.counts["accumulator_flops"] += v_n_tilde.numel() + 2 * self.product.numel()
             self.matmul.counts["matmul_flops"] += 2 * self.product.numel() * a_n_tilde.shape[-1]
+        residual = native.sub(v_n_tilde.contiguous(), v_delta_tilde.contiguous())
         native.bmm(a_n_tilde, v_delta_tilde, out=self.product, accumulate=True)
-        native.bmm(a_delta_tilde, native.sub(v_n_tilde.contiguous(), v_delta_tilde.contiguous()), out=self.product,
-                   accumulate=True)
+        native.bmm(a_delta_tilde, residual, out=self.product, accumulate=True)
         return self.product
-
-    def reset_self(self):
-        self.first = True
-        self.product = None
