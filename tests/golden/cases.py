@@ -14,6 +14,11 @@ SMALL_B = dict(depth=3, dim=768, heads=12, mlp_ratio=4, position_encoding_size=(
 SMALL_TC = dict(depth=3, dim=768, heads=12, mlp_ratio=4, position_encoding_size=(14, 14),
                 window_indices=(0, 2), window_size=(14, 14))
 
+# the full ViTDet-B backbone (12 blocks, 8 windowed + 4 global) at BASELINE.json configs[0]: 672 x 672 -> 42 x 42 tokens,
+# nine 14 x 14 windows without padding, global rel-pos tables interpolated from 64 to 42 entries, k = 512 of 1764
+VITDET_B_FULL = dict(depth=12, dim=768, heads=12, mlp_ratio=4, position_encoding_size=(14, 14),
+                     window_indices=(0, 1, 3, 4, 6, 7, 9, 10), window_size=(14, 14), relative_embedding_size=(64, 64))
+
 CASES = {
     # windowed (padded 7->8) + global eventful blocks, rel-pos with interpolated tables
     "tiny_vitdet": dict(cfg=TINY, input_size=(7, 7), batch=1, frames=5, policy=("topk", dict(k=12)),
@@ -51,6 +56,9 @@ CASES = {
     "small_vitdet_tc": dict(cfg=SMALL_TC, input_size=(8, 64), batch=2, frames=3, policy=("topk", dict(k=160)),
                             block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
                             std=0.04, stream="drift", seed=12, subsample=True),
+    "vitdet_b_672": dict(cfg=VITDET_B_FULL, input_size=(42, 42), batch=1, frames=3, policy=("topk", dict(k=512)),
+                         block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
+                         std=0.02, stream="drift", seed=13, subsample=True),
 }
 
 GATES = ("qkv_gate", "projection_gate", "mlp_gate")

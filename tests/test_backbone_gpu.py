@@ -57,7 +57,7 @@ def test_backbone_matches_oracle_given_identical_index_sets(name):
                 assert set(exact_free) == set(forced)
 
 
-@pytest.mark.parametrize("name", ["tiny_vitdet", "tiny_vivit", "small_vitdet_b", "small_vitdet_tc", "tiny_dense"])
+@pytest.mark.parametrize("name", ["tiny_vitdet", "tiny_vivit", "small_vitdet_b", "small_vitdet_tc", "tiny_dense", "vitdet_b_672"])
 def test_first_frame_matches_reference_fixture(name):
     """Frame 0 needs no selection: compare straight against the committed reference outputs."""
     case, gold = CASES[name], load_golden(name)
@@ -68,7 +68,7 @@ def test_first_frame_matches_reference_fixture(name):
     assert rel_err(got, want) < 0.04
 
 
-@pytest.mark.parametrize("name", ["tiny_vitdet", "small_vitdet_b", "small_vitdet_tc", "tiny_vivit"])
+@pytest.mark.parametrize("name", ["tiny_vitdet", "small_vitdet_b", "small_vitdet_tc", "tiny_vivit", "vitdet_b_672"])
 def test_counters_match_reference_fixture(name):
     case, gold = CASES[name], load_golden(name)
     model = build_gpu_backbone(case, case_params(case), DT)
