@@ -25,7 +25,7 @@ VITDET_B = dict(  # configs/models/vitdet_b_coco.yml
 
 
 def backbone_kwargs(cfg, input_size, block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
-                    matmul_2_cast=None, has_class_token=False):
+                    matmul_2_cast=None, has_class_token=False, pool_size=None):
     """kwargs for ViTBackbone(...) in the shape configs/models/*.yml feeds it (backbones.py:13-24)."""
     block_config = dict(dim=cfg["dim"], heads=cfg["heads"], mlp_ratio=cfg["mlp_ratio"])
     if cfg.get("relative_embedding_size") is not None:
@@ -34,6 +34,8 @@ def backbone_kwargs(cfg, input_size, block_class="EventfulBlock", windowed_class
         block_config["window_size"] = list(cfg["window_size"])
     if matmul_2_cast is not None:
         block_config["matmul_2_cast"] = matmul_2_cast
+    if pool_size is not None:
+        block_config["pool_size"] = list(pool_size)
     kw = dict(
         block_config=block_config,
         depth=cfg["depth"],

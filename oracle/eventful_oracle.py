@@ -229,8 +229,8 @@ def sized_position_encoding(encoding, encoding_size, input_size, has_class_token
     return e
 
 
-def relative_table(embedding, embedding_size, attention_size, dim):
-    """RelativePositionEmbedding._get_relative without pooling (utils.py:173-184)."""
+def relative_table(embedding, embedding_size, attention_size, dim, pool=None):
+    """RelativePositionEmbedding._get_relative (utils.py:173-189); `pool` averages the key axis (utils.py:185-188)."""
     s = embedding_size[dim]
     r0 = torch.arange(s).unsqueeze(1)
     r1 = torch.arange(s).unsqueeze(0)
@@ -239,16 +239,20 @@ def relative_table(embedding, embedding_size, attention_size, dim):
         rel = rel.transpose(0, 2).unsqueeze(0)
         rel = F.interpolate(rel, tuple(attention_size), mode="bicubic", align_corners=False)
         rel = rel.squeeze(0).transpose(0, 2)
+    if pool is not None:
+        rel = F.avg_pool1d(rel.transpose(1, 2), pool[dim]).transpose(1, 2)
     return rel
 
 
-def add_relative_position(x, q, y_rel, x_rel, attention_size, inplace):
+def add_relative_position(x, q, y_rel, x_rel, attention_size, inplace, key_size=None):
     """
     RelativePositionEmbedding.forward (utils.py:139-171): decomposed rel-pos
-    bias computed from the *unscaled* q and added to the logits x (B,H,N,N).
+    bias computed from the *unscaled* q and added to the logits x (B,H,N,Nk);
+    `key_size` is the pooled key grid when K/V pooling is on (utils.py:143-147).
     """
     a = tuple(attention_size)
-    xs = x.view(x.shape[:2] + a + a)
+    p = a if key_size is None else tuple(key_size)
+    xs = x.view(x.shape[:2] + a + p)
     qs = q.view(q.shape[:2] + a + q.shape[-1:])
     t = torch.einsum("abhwc,hkc->abhwk", qs, y_rel).unsqueeze(-1)
     if inplace:
@@ -256,7 +260,7 @@ def add_relative_position(x, q, y_rel, x_rel, attention_size, inplace):
     else:
         xs = xs + t
     xs += torch.einsum("abhwc,wkc->abhwk", qs, x_rel).unsqueeze(-2)
-    return xs.view(xs.shape[:2] + (prod(a), prod(a)))
+    return xs.view(xs.shape[:2] + (prod(a), prod(p)))
 
 
 # --------------------------------------------------------------------------
@@ -280,8 +284,8 @@ class OracleBackbone:
     ViTBackbone (backbones.py:8-64) + Block / EventfulTokenwiseBlock /
     EventfulMatmul1Block / EventfulBlock (blocks.py:26-575) as plain functions
     over a parameter dict that uses the reference's state-dict key names and a
-    per-block state dict.  ATS and K/V pooling (blocks.py:150-181,303-326) are
-    out of round-1 scope and not restated.
+    per-block state dict.  K/V pooling (blocks.py:303-326,525-540) is restated
+    (`pool_size`); ATS (blocks.py:150-181) is not.
     """
 
     def __init__(
@@ -303,6 +307,8 @@ class OracleBackbone:
         windowed_matmul_2_cast="same",
         gate_before_ln=False,
         stgt=False,
+        pool_size=None,
+        windowed_pool_size="same",
     ):
         self.w = params
         self.depth, self.dim, self.heads = depth, dim, heads
@@ -323,7 +329,11 @@ class OracleBackbone:
             rel = None
             if relative_embedding_size is not None:
                 rel = ws if ws is not None else tuple(relative_embedding_size)  # blocks.py:86-91
-            self.blocks.append(dict(cls=cls, window=ws, rel=rel, cast=cast))
+            pool = pool_size
+            if windowed and windowed_pool_size != "same":
+                pool = windowed_pool_size
+            pool = None if pool is None else tuple(pool)
+            self.blocks.append(dict(cls=cls, window=ws, rel=rel, cast=cast, pool=pool))
         self.policy = None
         self.reset()
 
@@ -410,12 +420,35 @@ class OracleBackbone:
         if blk["rel"] is None:
             return x
         att = blk["window"] if blk["window"] is not None else self.input_size
+        pool = blk["pool"]
         if i not in self._rel:  # cached until reset (utils.py:151-156,186-191)
             self._rel[i] = (
-                relative_table(self._p(i, "relative_position.y_embedding"), blk["rel"], att, 0),
-                relative_table(self._p(i, "relative_position.x_embedding"), blk["rel"], att, 1),
+                relative_table(self._p(i, "relative_position.y_embedding"), blk["rel"], att, 0, pool),
+                relative_table(self._p(i, "relative_position.x_embedding"), blk["rel"], att, 1, pool),
             )
-        return add_relative_position(x, q, self._rel[i][0], self._rel[i][1], att, inplace)
+        keys = None if pool is None else (att[0] // pool[0], att[1] // pool[1])
+        return add_relative_position(x, q, self._rel[i][0], self._rel[i][1], att, inplace, keys)
+
+    def _pool_tokens(self, i, x):
+        """Block._pool_tokens (blocks.py:303-326): average-pools k / v over the token grid."""
+        blk = self.blocks[i]
+        if blk["pool"] is None:
+            return x
+        w = blk["window"] if blk["window"] is not None else self.input_size
+        s = x.shape
+        x = x.reshape((-1,) + tuple(w) + s[-1:]).permute(0, 3, 1, 2)
+        x = F.avg_pool2d(x, blk["pool"]).permute(0, 2, 3, 1)
+        return x.reshape(s[:-2] + (-1,) + s[-1:])
+
+    def _pool_index(self, i, index):
+        """EventfulMatmul1Block._pool_index (blocks.py:525-540): token index -> sorted unique pooled-cell index."""
+        pool = self.blocks[i]["pool"]
+        if pool is None or index is None:
+            return index
+        width = self.input_size[1]
+        iy = index.div(width, rounding_mode="floor").div(pool[0], rounding_mode="floor")
+        ix = index.remainder(width).div(pool[1], rounding_mode="floor")
+        return (iy * (width // pool[1]) + ix).unique(dim=-1)
 
     @staticmethod
     def _cast(i_cast, a, v):
@@ -427,9 +460,10 @@ class OracleBackbone:
 
     # -- attention variants --------------------------------------------------------
     def _attention_dense(self, i, x):
-        """Block._forward_attention (blocks.py:205-240), ATS/pooling off."""
+        """Block._forward_attention (blocks.py:205-240), ATS off."""
         x = self._partition_windows(i, x)
         q, k, v = self._heads(x)
+        k, v = self._pool_tokens(i, k), self._pool_tokens(i, v)  # :216-217
         a = (q / self.scale) @ k.transpose(-2, -1)  # :223
         a = self._relpos(i, a, q, inplace=True)  # :225
         a = a.softmax(dim=-1)  # :226
@@ -440,13 +474,15 @@ class OracleBackbone:
         return x.to(old) if self.blocks[i]["cast"] is not None else x
 
     def _matmul_1(self, i, x, index):
-        """EventfulMatmul1Block._forward_matmul_1 (blocks.py:506-523), pooling off."""
+        """EventfulMatmul1Block._forward_matmul_1 (blocks.py:506-523)."""
         q, k, v = self._heads(x)
+        k, v = self._pool_tokens(i, k), self._pool_tokens(i, v)  # :509-510
+        index_k = self._pool_index(i, index)  # :511
         a = matmul_buffer(
-            self._st(i, "matmul_accumulator_1"), q / self.scale, k.transpose(-2, -1), index, index
+            self._st(i, "matmul_accumulator_1"), q / self.scale, k.transpose(-2, -1), index, index_k
         )
         a = self._relpos(i, a, q, inplace=False)  # :521
-        return a.softmax(dim=-1), v, index
+        return a.softmax(dim=-1), v, index_k
 
     def _attention_matmul1(self, i, x, index):
         """EventfulMatmul1Block._forward_attention (blocks.py:497-504)."""

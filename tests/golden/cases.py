@@ -19,6 +19,9 @@ SMALL_TC = dict(depth=3, dim=768, heads=12, mlp_ratio=4, position_encoding_size=
 VITDET_B_FULL = dict(depth=12, dim=768, heads=12, mlp_ratio=4, position_encoding_size=(14, 14),
                      window_indices=(0, 1, 3, 4, 6, 7, 9, 10), window_size=(14, 14), relative_embedding_size=(64, 64))
 
+# global blocks with interpolated rel-pos tables on a 6 x 6 grid: K / V pooled 2 x 2 -> 9 keys (oracle only)
+TINY_REL = dict(depth=2, dim=32, heads=2, mlp_ratio=4, position_encoding_size=(4, 4), relative_embedding_size=(5, 5))
+
 CASES = {
     # windowed (padded 7->8) + global eventful blocks, rel-pos with interpolated tables
     "tiny_vitdet": dict(cfg=TINY, input_size=(7, 7), batch=1, frames=5, policy=("topk", dict(k=12)),
@@ -56,6 +59,12 @@ CASES = {
     "small_vitdet_tc": dict(cfg=SMALL_TC, input_size=(8, 64), batch=2, frames=3, policy=("topk", dict(k=160)),
                             block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
                             std=0.04, stream="drift", seed=12, subsample=True),
+    "tiny_pool_dense": dict(cfg=TINY_REL, input_size=(6, 6), batch=2, frames=2, policy=None, block_class="Block",
+                            windowed_class=None, pool_size=(2, 2), std=0.08, stream="drift", seed=14),
+    "tiny_pool_matmul1": dict(cfg=TINY_REL, input_size=(6, 6), batch=1, frames=4, policy=("topk", dict(k=10)),
+                              block_class="EventfulMatmul1Block", pool_size=(2, 2), std=0.08, stream="drift", seed=15),
+    "tiny_pool_eventful": dict(cfg=TINY_REL, input_size=(6, 6), batch=1, frames=4, policy=("topk", dict(k=10)),
+                               block_class="EventfulBlock", pool_size=(2, 2), std=0.08, stream="drift", seed=16),
     "vitdet_b_672": dict(cfg=VITDET_B_FULL, input_size=(42, 42), batch=1, frames=3, policy=("topk", dict(k=512)),
                          block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
                          std=0.02, stream="drift", seed=13, subsample=True),

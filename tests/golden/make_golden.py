@@ -52,6 +52,7 @@ def reference_backbone(case):
         cfg, case["input_size"], block_class=case["block_class"],
         windowed_class=case.get("windowed_class", "EventfulTokenwiseBlock"),
         matmul_2_cast=case.get("matmul_2_cast"), has_class_token=case.get("has_class_token", False),
+        pool_size=case.get("pool_size"),
     )
     if kw.get("windowed_class") is None:
         kw.pop("windowed_class", None)

@@ -39,6 +39,7 @@ def oracle_for(case, params):
         matmul_2_cast=case.get("matmul_2_cast"),
         windowed_matmul_2_cast=(None if case.get("matmul_2_cast") else "same"),
         gate_before_ln=case.get("gate_before_ln", False), stgt=case.get("stgt", False),
+        pool_size=case.get("pool_size"),
     )
     if case["policy"] is not None:
         model.set_policy(case["policy"][0], **case["policy"][1])
