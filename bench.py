@@ -405,9 +405,6 @@ def main():
     torch.cuda.set_device(local)
     dist_ctx = None
     if world > 1:
-        # keep stdout to the single JSON line: NCCL prints its version banner there when NCCL_DEBUG is VERSION / INFO
-        if not os.environ.get("ET_BENCH_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
 
         # NCCL writes its version banner to fd 1 when the communicator is created (whatever NCCL_DEBUG the launcher

@@ -770,24 +770,9 @@ constexpr int apply_smem(int gh, int gw) {
     return (BQ * (DH + 8) + 3 * BKV * (DH + 8) + BKV * (BQ + 8) + BQ * (gh + 1 + gw + 1)) * (int)sizeof(T) + 16;
 }
 
-// Raises the dynamic-smem limit of a kernel once per (kernel, size high-water mark).
+// Raises the dynamic-smem limit of a kernel once per (kernel, device, size high-water mark).
 template <typename K>
-int set_smem(K kernel, int bytes) {
-    static const void* seen_fn[64];
-    static int seen_bytes[64];
-    static int n_seen = 0;
-    const void* key = reinterpret_cast<const void*>(kernel);
-    int slot = -1;
-    for (int i = 0; i < n_seen; ++i)
-        if (seen_fn[i] == key) slot = i;
-    if (slot >= 0 && seen_bytes[slot] >= bytes) return ET_OK;
-    if (bytes > 227 * 1024) return et_fail(ET_ERR_UNSUPPORTED, "kernel needs %d bytes of shared memory (> 227 KB)", bytes);
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return et_fail(ET_ERR_CUDA, "cudaFuncSetAttribute(%d bytes): %s", bytes, cudaGetErrorString(e));
-    if (slot < 0 && n_seen < 64) slot = n_seen++;
-    if (slot >= 0) { seen_fn[slot] = key; seen_bytes[slot] = bytes; }
-    return ET_OK;
-}
+int set_smem(K kernel, int bytes) { return et_raise_smem(kernel, bytes); }
 
 // every sub-buffer of the workspace starts on a 16-byte boundary (element counts rounded up to 8)
 inline size_t align8(size_t n) { return (n + 7) / 8 * 8; }

@@ -695,26 +695,15 @@ __global__ void __launch_bounds__(256) onehot_kernel(const long long* idx, uint1
     *reinterpret_cast<uint4*>(oh + (size_t)j * 128 + base) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-template <typename K>
-int raise_smem(K kernel, int bytes) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return et_fail(ET_ERR_CUDA, "cudaFuncSetAttribute(%d bytes): %s", bytes, cudaGetErrorString(e));
-    return ET_OK;
-}
 
 template <bool BF16>
 int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, int mode, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        int rc;
-        if ((rc = raise_smem(tc_stats_kernel<BF16>, ST_SMEM))) return rc;
-        if ((rc = raise_smem(tc_apply_kernel<BF16, ET_ATTN_DENSE>, AP_SMEM))) return rc;
-        if ((rc = raise_smem(tc_apply_kernel<BF16, ET_ATTN_FIRST>, AP_SMEM))) return rc;
-        if ((rc = raise_smem(tc_apply_kernel<BF16, ET_ATTN_DELTA>, AP_SMEM))) return rc;
-        configured = true;
-    }
-    CUtensorMap tm128, tm64, tmsel, tmbh, tmbw, tmoh;
     int rc;
+    if ((rc = et_raise_smem(tc_stats_kernel<BF16>, ST_SMEM))) return rc;
+    if ((rc = et_raise_smem(tc_apply_kernel<BF16, ET_ATTN_DENSE>, AP_SMEM))) return rc;
+    if ((rc = et_raise_smem(tc_apply_kernel<BF16, ET_ATTN_FIRST>, AP_SMEM))) return rc;
+    if ((rc = et_raise_smem(tc_apply_kernel<BF16, ET_ATTN_DELTA>, AP_SMEM))) return rc;
+    CUtensorMap tm128, tm64, tmsel, tmbh, tmbw, tmoh;
     if ((rc = make_tmap_2d(&tm128, qkv, (long long)a.B * a.N, 3LL * a.D, 128, a.is_bf16))) return rc;
     if ((rc = make_tmap_2d(&tm64, qkv, (long long)a.B * a.N, 3LL * a.D, 64, a.is_bf16))) return rc;
     tmbh = tmbw = tmoh = tm128;  // placeholders when there is no rel-pos bias (never dereferenced)

@@ -321,15 +321,10 @@ int et_tc_window_attention(const void* qkv, const void* pad_token, void* bias_co
     a.nwy = (gh + wh - 1) / wh; a.nwx = (gw + ww - 1) / ww; a.H = H; a.D = H * 64; a.Wn = wh * ww;
     a.NK = (a.Wn + 15) / 16 * 16; a.has_bias = has_bias; a.is_bf16 = is_bf16; a.c1 = 0.125f * kLog2e;
     const int nwin = a.nwx * a.nwy;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_window_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM);
-        if (e != cudaSuccess) return et_fail(ET_ERR_CUDA, "cudaFuncSetAttribute(window): %s", cudaGetErrorString(e));
-        configured = true;
-    }
-    CUtensorMap tq, tb, toh;
     int rc;
+    if ((rc = et_raise_smem(tc_window_kernel<true>, W_SMEM))) return rc;
+    if ((rc = et_raise_smem(tc_window_kernel<false>, W_SMEM))) return rc;
+    CUtensorMap tq, tb, toh;
     if ((rc = make_tmap_grid4d(&tq, qkv, B, gh, gw, 3 * a.D, wh, ww, is_bf16))) return rc;
     tb = toh = tq;
     if (has_bias) {

@@ -214,6 +214,14 @@ inline void et_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through ET_CHECK_LAUNCH
 }
 
+// ---------------------------------------------------------------- per-device host state
+// SM count of the CURRENT device and "this kernel may use `bytes` of dynamic shared memory on the current device":
+// both cached per device (a process may drive several GPUs) behind a mutex (calls may come from several host threads).
+int et_sm_count();
+int et_raise_smem_impl(const void* kernel, int bytes);
+template <typename K>
+inline int et_raise_smem(K kernel, int bytes) { return et_raise_smem_impl(reinterpret_cast<const void*>(kernel), bytes); }
+
 // Number of kernels this library has enqueued (bench.py reports it as gpu_launches).
 extern long long g_et_launches;
 #define ET_COUNT_LAUNCH(n) (g_et_launches += (n))

@@ -8,11 +8,52 @@
 //   buffer_scatter      : TokenBuffer row / column scatter
 //   add                 : residual add
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 #include "et_common.cuh"
 
 thread_local char g_et_error[512] = "";
 long long g_et_launches = 0;
+
+namespace {
+constexpr int kMaxDevices = 64;
+std::mutex g_dev_mutex;
+int g_sm_count[kMaxDevices];
+struct SmemGrant { const void* fn; int device; int bytes; };
+std::vector<SmemGrant> g_smem_grants;
+}  // namespace
+
+int et_sm_count() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    if (g_sm_count[dev] == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        g_sm_count[dev] = sms;
+    }
+    return g_sm_count[dev];
+}
+
+int et_raise_smem_impl(const void* kernel, int bytes) {
+    if (bytes > 227 * 1024) return et_fail(ET_ERR_UNSUPPORTED, "kernel needs %d bytes of shared memory (> 227 KB)", bytes);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    for (SmemGrant& g : g_smem_grants)
+        if (g.fn == kernel && g.device == dev) {
+            if (g.bytes >= bytes) return ET_OK;
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            if (e != cudaSuccess) return et_fail(ET_ERR_CUDA, "cudaFuncSetAttribute(%d bytes): %s", bytes, cudaGetErrorString(e));
+            g.bytes = bytes;
+            return ET_OK;
+        }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return et_fail(ET_ERR_CUDA, "cudaFuncSetAttribute(%d bytes): %s", bytes, cudaGetErrorString(e));
+    g_smem_grants.push_back({kernel, dev, bytes});
+    return ET_OK;
+}
 int g_gate_cta_waves = 2;  // CTAs of the gate kernels per SM over the whole launch (et_debug_set key 10)
 int g_et_pdl = []() { const char* e = getenv("EVENTFUL_B200_PDL"); return (e && e[0] == '1') ? 1 : 0; }();
 
@@ -639,7 +680,7 @@ struct ReplaceLauncher {
 
 int grid_for(long long work_items, int threads) {
     long long blocks = (work_items + threads - 1) / threads;
-    const long long cap = 148LL * 16;
+    const long long cap = (long long)et_sm_count() * 16;
     return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
@@ -697,7 +738,7 @@ int et_gate_select(const void* xa, const void* xb, void* xsum_out, const void* l
         const int lpt = nchunks <= 1 ? 1 : nchunks <= 2 ? 2 : nchunks <= 4 ? 4 : nchunks <= 8 ? 8 : nchunks <= 16 ? 16 : 32;
         const int groups = kGateThreads / lpt;
         // ~4 CTAs per SM over the whole launch (all resident: more loads in flight), each CTA at least one pass
-        long long want = (g_gate_cta_waves * 148 + R - 1) / R;
+        long long want = ((long long)g_gate_cta_waves * et_sm_count() + R - 1) / R;
         long long max_ctas = (N + groups - 1) / groups;
         long long ctas = want < 1 ? 1 : (want > max_ctas ? max_ctas : want);
         a.tokens_per_cta = (int)((N + ctas - 1) / ctas);

@@ -550,15 +550,10 @@ linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 template <int BLOCK_N, int STAGES, int MH = 1>
 int launch_linear(const void* A, const void* W, const LinearArgs& args, cudaStream_t stream) {
     using L = GemmSmem<BLOCK_N, STAGES, MH>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(linear_tcgen05_kernel<BLOCK_N, STAGES, MH>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-        if (e != cudaSuccess) return et_fail(ET_ERR_CUDA, "et_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
-    }
+    int rc = et_raise_smem(linear_tcgen05_kernel<BLOCK_N, STAGES, MH>, L::TOTAL);
+    if (rc) return rc;
     CUtensorMap ta, tw;
-    int rc = make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M * MH, args.is_bf16);
+    rc = make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M * MH, args.is_bf16);
     if (rc) return rc;
     rc = make_tmap_2d(&tw, W, args.n_feat, args.K, BLOCK_N, args.is_bf16);
     if (rc) return rc;
@@ -571,17 +566,11 @@ int launch_linear(const void* A, const void* W, const LinearArgs& args, cudaStre
 template <int BLOCK_N, int STAGES>
 int launch_persistent(const void* A, const void* W, const LinearArgs& args, cudaStream_t stream) {
     using L = PersistSmem<BLOCK_N, STAGES>;
-    static int sms = 0;
-    if (sms == 0) {
-        cudaError_t e = cudaFuncSetAttribute(linear_persistent_kernel<BLOCK_N, STAGES>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-        if (e != cudaSuccess) return et_fail(ET_ERR_CUDA, "et_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    int rc = et_raise_smem(linear_persistent_kernel<BLOCK_N, STAGES>, L::TOTAL);
+    if (rc) return rc;
+    const int sms = et_sm_count();
     CUtensorMap ta, tw;
-    int rc = make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M, args.is_bf16);
+    rc = make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M, args.is_bf16);
     if (rc) return rc;
     rc = make_tmap_2d(&tw, W, args.n_feat, args.K, BLOCK_N, args.is_bf16);
     if (rc) return rc;
@@ -672,7 +661,8 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
     a.n_out_rows = (int)n_out_rows; a.is_bf16 = dtype == ET_BF16;
     a.prof = g_gemm_prof;
 
-    // Tile width: minimise waves(tiles over 148 SMs) x per-tile cost (~ BLOCK_N + fixed overhead).
+    // Tile width: minimise waves(tiles over the SMs of this device) x per-tile cost (~ BLOCK_N + fixed overhead).
+    const long long sms = et_sm_count();
     const int candidates[5] = {256, 192, 128, 96, 64};
     int best = 64;
     double best_cost = 1e30;
@@ -681,8 +671,8 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
         const int bn = candidates[c];
         if (bn > 64 && bn >= 2 * n_feat) continue;
         const long long tiles = mt * ((n_feat + bn - 1) / bn);
-        const long long slots = tiles > 148 ? 296 : 148;  // two CTAs per SM with the shallow pipelines
-        const double cost = (double)((tiles + slots - 1) / slots) * (bn + 32) * (tiles > 148 ? 1.25 : 1.0);
+        const long long slots = tiles > sms ? 2 * sms : sms;  // two CTAs per SM with the shallow pipelines
+        const double cost = (double)((tiles + slots - 1) / slots) * (bn + 32) * (tiles > sms ? 1.25 : 1.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
     }
     if (g_force_block_n) best = g_force_block_n;
@@ -692,7 +682,7 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
     // smem so two CTAs share an SM: the epilogue of one overlaps the mainloop of the other and a launch of up to 296
     // tiles is a single wave).  Shallow is used when the tile count exceeds one CTA-per-SM wave.
     const long long tiles_best = mt * ((n_feat + best - 1) / best);
-    const bool shallow = g_force_depth ? g_force_depth == 2 : tiles_best > 148;
+    const bool shallow = g_force_depth ? g_force_depth == 2 : tiles_best > sms;
     // 256-row CTA tiles (two 128-row accumulators sharing one W tile, one CTA per SM): a third less operand traffic from
     // L2, but no second CTA whose mainloop hides the epilogue.  Measured (profiles/r1_gemm_sweep.txt): only long-K
     // layers of multi-stream batches gain (mlp_2 at M = 16384: 84 -> 80 us); everything else keeps 128-row tiles.
@@ -701,7 +691,7 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
         const int pbn = g_force_block_n == 128 || g_force_block_n == 192 ? g_force_block_n : 256;
         const long long ptiles = mt * ((n_feat + pbn - 1) / pbn);
         const bool long_k = K >= 2048;  // long-K layers do better with 256-row tiles (below)
-        const bool persist = g_force_persist ? g_force_persist == 1 : (ptiles >= 2 * 148 && g_force_mh == 0 && !long_k);
+        const bool persist = g_force_persist ? g_force_persist == 1 : (ptiles >= 2 * sms && g_force_mh == 0 && !long_k);
         if (persist) {
             switch (pbn) {
                 case 128: rc = launch_persistent<128, 5>(A, W, a, s); break;

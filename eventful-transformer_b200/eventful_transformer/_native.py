@@ -135,7 +135,10 @@ _tickets = {}
 
 
 def _ticket(device, rows):
-    key = device.index  # one launch sequence per device at a time (single stream per backbone)
+    # The last-CTA ticket of et_gate_select is a self-resetting counter per gate row: launches that may run
+    # concurrently must not share it, so the workspace is keyed by (device, CUDA stream).  (Kernels of one stream
+    # are ordered; a captured graph keeps the tensor of the stream it was captured on.)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     t = _tickets.get(key)
     if t is None or t.numel() < rows:
         t = torch.zeros(max(rows, 64), dtype=torch.int32, device=device)
@@ -201,6 +204,8 @@ def gate_gather(x, idx, p=None, ln=None, eps=1e-6, ln_after=False, want_delta=Fa
     rows = 1
     for s in lead:
         rows *= s
+    if p is not None:
+        _dense(p, "gate state")
     c_tilde = torch.empty(lead + (k, d), dtype=x.dtype, device=x.device)
     e_tilde = torch.empty_like(c_tilde) if want_delta else None
     ln_w, ln_b = (None, None) if ln is None else ln
@@ -216,6 +221,8 @@ def gate_gather_cols(c, idx, p=None, want_delta=False):
     """Column gate on c (..., N, M) with idx (B, k) shared by all rows of a batch entry."""
     require_device(c)
     _dense(c, "gate input")
+    if p is not None:
+        _dense(p, "gate state")
     n, m, k = c.shape[-2], c.shape[-1], idx.shape[-1]
     rows = c.numel() // (n * m)
     rpi = rows // (idx.numel() // k)

@@ -41,6 +41,9 @@ class ViTBackbone(ExtendedModule):
             self.blocks.append(getattr(blocks, name)(input_size=input_size, **config))
         # CUDA-graph replay of incremental frames (opt-in: attribute or EVENTFUL_B200_GRAPH=1)
         self.use_cuda_graph = os.environ.get("EVENTFUL_B200_GRAPH", "0") == "1"
+        # A replayed graph writes its result into one static tensor.  By default the caller gets a copy (safe to keep
+        # across frames); set False to receive the static tensor itself (valid until the next forward) and save the copy.
+        self.clone_graph_output = True
         self._graph = None
         self._graph_key = None
         self._static_in = None
@@ -105,4 +108,4 @@ class ViTBackbone(ExtendedModule):
             self._static_in.copy_(x)
         self._graph.replay()
         self._frames_seen += 1
-        return self._static_out.clone()
+        return self._static_out.clone() if self.clone_graph_output else self._static_out

@@ -41,15 +41,13 @@ LN_EPS = 1e-6
 # single-pass attention kernel is used for dense attention over at most this many keys
 _SMALL_ATTENTION = 512
 
-_identity_cache = {}
-
-
-def _identity_index(batch, n, device):
+def _identity_index(cache, batch, n, device):
+    """arange(n) per batch entry, cached per block instance until reset() (a captured CUDA graph may hold it)."""
     key = (batch, n, device)
-    idx = _identity_cache.get(key)
+    idx = cache.get(key)
     if idx is None:
         idx = torch.arange(n, device=device, dtype=torch.int64).repeat(batch, 1).contiguous()
-        _identity_cache[key] = idx
+        cache[key] = idx
     return idx
 
 
@@ -61,6 +59,7 @@ class Block(ExtendedModule):
         super().__init__()
         self.heads = heads
         self.input_size = tuple(input_size)
+        self._identity = {}
         if ats_fraction is not None:
             assert pool_size is None
             assert window_size is None
@@ -108,12 +107,23 @@ class Block(ExtendedModule):
 
     def reset_self(self):
         self.last_ats_indices = None
+        self._identity = {}
 
     # ------------------------------------------------------------------ shared helpers
     def _check_input(self, x):
         native.require_device(x)
-        if self.training and isinstance(self.drop_path, DropPath):
-            raise NotImplementedError("eventful_b200 is an inference path: drop-path is identity (call .eval())")
+        if x.dtype not in native._DTYPES:
+            raise TypeError(f"eventful_b200: unsupported activation dtype {x.dtype} (float32, bfloat16, float16)")
+        if self.qkv.weight.dtype != x.dtype:
+            raise TypeError(f"eventful_b200: the input is {x.dtype} but the block's parameters are "
+                            f"{self.qkv.weight.dtype}; cast the model or the input")
+        if self.training:
+            raise NotImplementedError("eventful_b200 is an inference path (no autograd through the kernels, drop-path "
+                                      "is identity): call .eval()")
+        if torch.is_grad_enabled() and (x.requires_grad or self.qkv.weight.requires_grad):
+            raise RuntimeError("eventful_b200 is an inference path: its kernels record no autograd graph, so gradients "
+                               "would silently be missing. Run under torch.inference_mode() / torch.no_grad() "
+                               "(as scripts/time/vitdet_vid.py:28 of the reference does) or freeze the parameters.")
         cast = self.matmul_2_cast
         if cast is not None and getattr(torch, cast) != x.dtype:
             raise NotImplementedError(
@@ -126,7 +136,7 @@ class Block(ExtendedModule):
 
     def _layer_norm_all(self, ln, x):
         """Dense LayerNorm over every token (rows gathered with the identity index)."""
-        idx = _identity_index(x.shape[0], x.shape[1], x.device)
+        idx = _identity_index(self._identity, x.shape[0], x.shape[1], x.device)
         out, _ = native.gate_gather(x, idx, ln=self._ln_params(ln), eps=ln.eps)
         return out
 

@@ -97,7 +97,10 @@ class _GateBase(_FrameState):
         return self.forward_first(c) if self.first else self.forward_incremental(c, forced_index=forced_index)
 
     def forward_first(self, c):
-        self.first, self.p = False, c
+        # p aliases the first input (modules.py:140) when that input is dense; a strided view (e.g. the v-gate's
+        # clone of a head-partitioned tensor, blocks.py:566) is materialised once, because the gate kernels address
+        # the state as a dense (..., N, D) array
+        self.first, self.p = False, (c if c.is_contiguous() else c.contiguous())
         return self._pack(c, None, None)
 
     def forward_incremental(self, c, forced_index=None):
@@ -130,7 +133,7 @@ class SimpleSTGTGate(_FrameState):
 
     def forward(self, c):
         if self.first:
-            self.first, self.p = False, c
+            self.first, self.p = False, (c if c.is_contiguous() else c.contiguous())
             return c, None
         self._tally("gate_flops", c.numel())
         c = c.contiguous()

@@ -335,6 +335,7 @@ class OracleBackbone:
             pool = None if pool is None else tuple(pool)
             self.blocks.append(dict(cls=cls, window=ws, rel=rel, cast=cast, pool=pool))
         self.policy = None
+        self.record_free = False
         self.reset()
 
     # -- control API (base.py:130-135, utils/misc.py:140-143) ----------------
@@ -343,6 +344,7 @@ class OracleBackbone:
         self._pos = None
         self._rel = {}
         self.trace = []
+        self.free_trace = []
 
     def set_policy(self, kind, **kw):
         self.policy = make_policy(kind, **kw)
@@ -371,6 +373,11 @@ class OracleBackbone:
             f = None
             if forced is not None and "p" in st:
                 f = forced.get((i, name))
+            if f is not None and self.record_free:
+                # checker aid: what the policy WOULD select here on the oracle's own (replayed-history) inputs,
+                # plus the norms, so a test can show that a CUDA selection differs only at near-ties
+                e = c - st["p"]
+                self.free_trace.append(((i, name), self.policy(e, dim=-1), token_norm(e, dim=-1)))
             out = token_gate(st, c, policy=self.policy, forced_index=f)
         if out[1] is not None:
             self.trace.append(((i, name), out[1]))
@@ -563,6 +570,7 @@ class OracleBackbone:
         compare activations given identical index sets).
         """
         self.trace = []
+        self.free_trace = []
         if self._pos is None:  # utils.py:53-67
             self._pos = sized_position_encoding(
                 self.w["position_encoding.encoding"],

@@ -68,6 +68,11 @@ CASES = {
     "vitdet_b_672": dict(cfg=VITDET_B_FULL, input_size=(42, 42), batch=1, frames=3, policy=("topk", dict(k=512)),
                          block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
                          std=0.02, stream="drift", seed=13, subsample=True),
+    # the BENCHMARKED configuration (BASELINE configs[1]): 1024 x 1024 -> 64 x 64 tokens, 25 padded 14 x 14 windows,
+    # k = 2048 of 4096; 4 frames so that the CUDA-graph path (captured at frame 2) is replayed at least once
+    "vitdet_b_1024": dict(cfg=VITDET_B_FULL, input_size=(64, 64), batch=1, frames=4, policy=("topk", dict(k=2048)),
+                          block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
+                          std=0.02, stream="drift", seed=17, subsample=True),
 }
 
 GATES = ("qkv_gate", "projection_gate", "mlp_gate")

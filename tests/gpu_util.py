@@ -56,3 +56,68 @@ def one_block_oracle(params, dim, heads, input_size, cls, window=None, rel=None,
                               position_encoding_size=input_size, block_class=cls, windowed_class=cls,
                               window_indices=(0,) if window else (), window_size=window,
                               relative_embedding_size=rel, has_class_token=has_class_token)
+
+
+# ------------------------------------------------------------------------------------------
+# measured-parity log: every GPU parity test records what it measured (not just pass / fail);
+# gpurun brings gpurun_out/ back, and the numbers are quoted in DESIGN.md / profiles/.
+# ------------------------------------------------------------------------------------------
+import json
+import os
+
+_PARITY_LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_measured.jsonl")
+
+
+def record(test, **values):
+    try:
+        os.makedirs(os.path.dirname(_PARITY_LOG), exist_ok=True)
+        with open(_PARITY_LOG, "a") as f:
+            f.write(json.dumps(dict(test=test, **values)) + "\n")
+    except OSError:
+        pass
+
+
+def elem_err(got, want):
+    """Per-element error statistics: (max |got - want|, max |got - want| / (atol_unit + |want|), rms(want))."""
+    got, want = got.float(), want.float()
+    diff = (got - want).abs()
+    rms = float(want.pow(2).mean().sqrt())
+    return float(diff.max()), float((diff / (rms + want.abs())).max()), rms
+
+
+def allclose_report(got, want, rtol, atol_rms, what):
+    """|got - want| <= atol_rms * rms(want) + rtol * |want| per element; returns the measured worst ratio."""
+    got, want = got.float(), want.float()
+    rms = float(want.pow(2).mean().sqrt())
+    bound = atol_rms * rms + rtol * want.abs()
+    ratio = float(((got - want).abs() / bound).max())
+    assert ratio <= 1.0, f"{what}: worst |err| / (atol + rtol |want|) = {ratio:.3f} (rtol={rtol}, atol={atol_rms} x rms={rms:.4f})"
+    return ratio
+
+
+def selection_agreement(gpu_index, free_index, norm, threshold=None):
+    """
+    Compares a CUDA selection with the oracle's own selection on (near-)identical inputs.
+    Returns (overlap fraction |A & B| / max(|A|, |B|), worst relative distance of a token in the symmetric difference
+    from the decision boundary: the k-th largest norm for top-k policies, the threshold for TokenNormThreshold).
+    """
+    lead = norm.shape[:-1]
+    rows = 1
+    for s_ in lead:
+        rows *= s_
+    gi = gpu_index.reshape(rows, -1)
+    fi = free_index.reshape(rows, -1)
+    nr = norm.reshape(rows, -1).float()
+    overlap, worst = 1.0, 0.0
+    for r in range(rows):
+        a, b = set(gi[r].tolist()), set(fi[r].tolist())
+        assert len(a) == gi.shape[-1], "CUDA selection holds duplicate indices"
+        if threshold is None:
+            assert len(a) == len(b)
+        if not a and not b:
+            continue
+        edge = float(threshold) if threshold is not None else float(nr[r].topk(len(b))[0][-1])
+        overlap = min(overlap, len(a & b) / max(len(a), len(b)))
+        for t in a ^ b:
+            worst = max(worst, abs(float(nr[r, t]) - edge) / max(edge, 1e-30))
+    return overlap, worst

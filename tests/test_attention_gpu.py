@@ -6,7 +6,7 @@ import torch
 import eventful_oracle as orc
 from eventful_transformer import _native as native
 from eventful_transformer import blocks
-from gpu_util import DEV, one_block_oracle, rel_err
+from gpu_util import DEV, one_block_oracle, record, rel_err
 
 pytestmark = pytest.mark.gpu
 DT = torch.bfloat16
@@ -36,6 +36,7 @@ WINDOW_CASES = [  # dim, heads, grid, window, rel size, batch
     (768, 12, (28, 28), (14, 14), (64, 64), 1),   # no padding
     (32, 2, (7, 7), (4, 4), (5, 5), 3),           # dh = 16, padding 7 -> 8
     (64, 2, (9, 5), (3, 5), (4, 4), 2),           # dh = 32, rectangular
+    (768, 12, (64, 64), (14, 14), (64, 64), 1),   # the benchmarked shape: 1024^2 -> 64 x 64 tokens, 25 windows padded 64 -> 70
 ]
 
 
@@ -72,6 +73,7 @@ GLOBAL_CASES = [  # dim, heads, grid, rel, extra tokens, k, batch
     (768, 12, (14, 14), None, 1, 64, 3),          # ViViT shape: 197 tokens incl. class token, batch of views
     (32, 2, (7, 7), (5, 5), 0, 12, 2),            # dh = 16, N not a multiple of 8
     (128, 2, (24, 24), (24, 24), 0, 576, 1),      # k == N (refresh everything)
+    (768, 12, (64, 64), (64, 64), 0, 2048, 1),    # the benchmarked shape: tc_stats / tc_apply with rel-pos at N = 4096, k = 2048
 ]
 
 
@@ -176,3 +178,37 @@ def test_tensor_core_window_path_agrees_with_mma_sync_path(grid, batch):
     finally:
         native.lib().et_debug_set(2, 1)
     assert rel_err(outs[0], outs[1]) < 1.5e-2
+
+
+def test_delta_accumulator_does_not_drift_over_32_frames():
+    """
+    The tcgen05 apply kernel accumulates  acc += a_n . v_n - p . (v_n - dV)  in fp32 and rounds acc to bf16 once per
+    frame, where the reference adds the two bf16-rounded products a_n . dV and dA . (v_n - dV) (modules.py:293-294).
+    Algebraically equal; this test follows both for 32 incremental frames on the same inputs and index sets and
+    requires that the distance to the exact-arithmetic oracle does not grow.
+    """
+    dim, heads, grid, k, frames = 768, 12, (8, 64), 160, 32
+    rel = (8, 64)
+    n = grid[0] * grid[1]
+    params = block_params(dim, heads, rel, seed=29, std=0.2)
+    g = torch.Generator().manual_seed(12)
+    oracle = one_block_oracle(params, dim, heads, grid, orc.EVENTFUL, rel=rel)
+    blk = gpu_block("EventfulBlock", dim, heads, grid, params, rel=rel)
+    qkv = torch.randn(1, n, 3 * dim, generator=g).to(DT)
+    buf_cpu, buf_gpu = qkv.float().clone(), qkv.to(DEV).clone()
+    want = oracle._attention_eventful(0, buf_cpu, None)
+    got = blk._attention_first(buf_gpu, None)
+    errs = [rel_err(got.cpu(), want)]
+    for t in range(1, frames + 1):
+        idx = torch.randperm(n, generator=g)[:k].view(1, k)
+        rows = (buf_cpu.gather(1, idx.unsqueeze(-1).expand(-1, -1, 3 * dim))
+                + 0.3 * torch.randn(1, k, 3 * dim, generator=g)).to(DT)
+        buf_cpu.scatter_(1, idx.unsqueeze(-1).expand(-1, -1, 3 * dim), rows.float())
+        buf_gpu.scatter_(1, idx.to(DEV).unsqueeze(-1).expand(-1, -1, 3 * dim), rows.to(DEV))
+        want = oracle._attention_eventful(0, buf_cpu, idx)
+        got = blk._attention_incremental(buf_gpu, idx.to(DEV))
+        errs.append(rel_err(got.cpu(), want))
+    record("delta_accumulator_drift", errors=[round(e, 5) for e in errs])
+    assert max(errs) < 3e-2, errs
+    # acc is stored in bf16 (as in the reference): rounding once per frame is a random walk ~ sqrt(frames) x 2^-9, nothing faster
+    assert max(errs[-8:]) <= 2.5 * max(errs[1:9]) + 3e-3, errs
