@@ -20,6 +20,13 @@ int et_tc_global_attention(const void* qkv, const void* sel, void* onehot, const
                            int NP, int H, int gh, int gw, int is_bf16, cudaStream_t stream);
 int et_tc_window_attention(const void* qkv, const void* pad_token, void* bias_comb, void* out, int B, int N, int gh, int gw,
                            int wh, int ww, int H, int has_bias, int is_bf16, cudaStream_t s);
+int et_generic_window_attention(const void* qkv, const void* pad_token, const void* rel_y, const void* rel_x, void* out,
+                                float* stats, int B, int N, int gh, int gw, int wh, int ww, int H, int dh, int dtype,
+                                cudaStream_t s);
+int et_generic_global_attention(const void* qkv, const void* kv_pooled, int pool_h, int pool_w, const void* rel_y,
+                                const void* rel_x, int mode, const int64_t* idx, const int32_t* count, int k, void* a_state,
+                                void* v_state, void* acc, void* out, float* stats, void* ws, int B, int N, int gh, int gw,
+                                int H, int dh, int dtype, int state_dtype, cudaStream_t s);
 int g_attn_tc = 1;  // et_debug_set(2, 0) forces the mma.sync kernels (tests compare the two paths)
 
 namespace {
@@ -39,6 +46,7 @@ struct AttnArgs {
     float rscale;
     // eventful part
     const long long* idx;
+    const int* count;  // device-side number of valid entries of idx per batch entry (or null: all k)
     int k, mode;
     void* a_state;
     void* acc;
@@ -570,7 +578,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_apply_kernel(const AttnArgs
     const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
     const int D = a.H * DH;
     const T* qkv = static_cast<const T*>(a.qkv);
-    const int nkeys = (MODE == ET_ATTN_DELTA) ? a.k : a.N;
+    const int nkeys = (MODE == ET_ATTN_DELTA) ? (a.count != nullptr ? min(a.k, a.count[b]) : a.k) : a.N;
     auto row_ptr = [&](int t, int part) -> const T* {
         return t < a.N ? qkv + ((size_t)b * a.N + t) * 3 * D + part * D + h * DH : nullptr;
     };
@@ -734,8 +742,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_apply_kernel(const AttnArgs
 // ---------------------------------------------------------------- v gate
 // DELTA: for each selected row: dV = v - p_v, Vd = v - dV, p_v = v.   FIRST: p_v = v for every token.
 template <typename T>
-__global__ void __launch_bounds__(256) vgate_kernel(const T* qkv, T* v_state, const long long* idx, T* Ksel, T* dV, T* Vd,
-                                                    int N, int D, int k, long long total_vec, int emit_vn) {
+__global__ void __launch_bounds__(256) vgate_kernel(const T* qkv, T* v_state, const long long* idx, const int* count, T* Ksel, T* dV,
+                                                    T* Vd, int N, int D, int k, long long total_vec, int emit_vn) {
     et_pdl_prologue();
     const int nch = D / 8;
     for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total_vec;
@@ -743,6 +751,7 @@ __global__ void __launch_bounds__(256) vgate_kernel(const T* qkv, T* v_state, co
         const int ch = (int)(gi % nch);
         const long long row = gi / nch;
         const long long b = row / k;
+        if (count != nullptr && row - b * k >= count[b]) continue;
         const long long tok = idx != nullptr ? idx[row] : row % k;
         const size_t src = ((size_t)b * N + tok) * 3 * D + 2 * D + (size_t)ch * 8;
         const size_t st = ((size_t)b * N + tok) * D + (size_t)ch * 8;
@@ -818,7 +827,8 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     AttnArgs args = a;
     const int D = a.H * DH;
     // tensor-core path: dh = 64, 128-row query blocks, rel-pos bias only for the 64-wide grid
-    const bool use_tc = DH == 64 && a.N % 128 == 0 && (rel_y == nullptr || (a.gw == 64 && a.gh <= 64)) && g_attn_tc;
+    const bool use_tc = DH == 64 && a.N % 128 == 0 && (rel_y == nullptr || (a.gw == 64 && a.gh <= 64)) && g_attn_tc &&
+                        a.count == nullptr;  // a device-side key count runs on the mma.sync kernels
     // workspace layout: [bias_h | bias_w | K_sel | dV | Vd | onehot]; the tc path pads bias rows to 64 columns
     const size_t ldh = use_tc ? 64 : a.gh, ldw = use_tc ? 64 : a.gw;
     T* bh = static_cast<T*>(ws);
@@ -837,7 +847,7 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     if (a.mode == ET_ATTN_DELTA) {
         const long long total = (long long)a.B * a.k * (D / 8);
         if (total > 0)
-            et_launch(vgate_kernel<T>, dim3((int)((total + 255) / 256)), dim3(256), 0, s, qkv, static_cast<T*>(v_state), a.idx,
+            et_launch(vgate_kernel<T>, dim3((int)((total + 255) / 256)), dim3(256), 0, s, qkv, static_cast<T*>(v_state), a.idx, a.count,
                                                                       use_tc ? Ksel : nullptr, dV, Vd, a.N, D, a.k, total,
                                                                       use_tc ? 1 : 0);
         ET_COUNT_LAUNCH(1);
@@ -846,7 +856,7 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     } else if (a.mode == ET_ATTN_FIRST) {
         const long long total = (long long)a.B * a.N * (D / 8);
         et_launch(vgate_kernel<T>, dim3((int)((total + 255) / 256)), dim3(256), 0, s, qkv, static_cast<T*>(v_state), nullptr, nullptr, nullptr,
-                                                                  nullptr, a.N, D, a.N, total, 0);
+                                                                  nullptr, nullptr, a.N, D, a.N, total, 0);
         ET_COUNT_LAUNCH(1);
     }
     if (use_tc) {
@@ -889,30 +899,49 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
 
 extern "C" {
 
-// Bytes of caller-provided scratch needed by et_window_attention / et_global_attention.
+// Bytes of caller-provided scratch needed by et_window_attention / et_global_attention (an upper bound over every
+// code path: tensor-core layouts, the mma.sync tables, and the general-precision path's fp32 statistics / v-gate deltas).
 int64_t et_attn_workspace_bytes(int64_t B, int64_t N, int64_t gh, int64_t gw, int64_t wh, int64_t ww, int64_t heads,
                                 int64_t dh, int64_t k, int has_relpos) {
-    int64_t elems = 0;
+    int64_t elems = 0, extra = 0;
     if (wh > 0) {
         const int64_t nw = ((gh + wh - 1) / wh) * ((gw + ww - 1) / ww);
         if (has_relpos) elems += align8(B * nw * heads * wh * ww * wh) + align8(B * nw * heads * wh * ww * ww);
         if (has_relpos) elems += B * nw * heads * 256 * 64 + 256 * 64;  // tensor-core layout: combined bias rows + one-hot block
+        extra = B * nw * heads * wh * ww * 2 * 4;                       // general path: (max, sum) per query row, fp32
     } else {
         // upper bound over both layouts (the tensor-core path pads bias rows to 64 columns and adds a one-hot scratch)
         if (has_relpos) elems += align8(B * heads * N * (gh > 64 ? gh : 64)) + align8(B * heads * N * (gw > 64 ? gw : 64));
         elems += 3 * align8(B * k * heads * dh);
         elems += ((B * k > N) ? B * k : N) * 128;
+        extra = B * heads * N * 2 * 4;  // statistics of the small single-window case
     }
-    return elems * 2 + 256;
+    return elems * 2 + extra + 512;
 }
 
 int et_window_attention(const void* qkv, const void* pad_token, const void* rel_y, const void* rel_x, void* out,
                            void* workspace, int64_t B, int64_t N, int64_t gh, int64_t gw, int64_t wh, int64_t ww,
                            int64_t heads, int64_t dh, int dtype, void* stream) {
     ET_CHECK_ARG(qkv && out, "et_window_attention: null pointer");
-    ET_CHECK_ARG(dtype == ET_BF16 || dtype == ET_F16, "et_window_attention: bf16 / fp16 only (dtype=%d)", dtype);
+    ET_CHECK_ARG(dtype == ET_BF16 || dtype == ET_F16 || dtype == ET_F32, "et_window_attention: bad dtype %d", dtype);
     ET_CHECK_ARG((rel_y == nullptr) == (rel_x == nullptr), "et_window_attention: rel_y / rel_x both or neither");
-    ET_CHECK_ARG(rel_y == nullptr || workspace != nullptr, "et_window_attention: rel-pos needs a workspace");
+    ET_CHECK_ARG((rel_y == nullptr && dtype != ET_F32) || workspace != nullptr, "et_window_attention: workspace required");
+    if (dtype == ET_F32) {  // general-precision path (et_generic.cu): fp32 arithmetic on the CUDA cores
+        ET_CHECK_ARG(dh <= 64, "et_window_attention (fp32): head dim %lld > 64", (long long)dh);
+        ET_CHECK_ARG(wh == 0 || (gh * gw == N && ww > 0), "et_window_attention: windowed attention needs N == gh * gw");
+        ET_CHECK_ARG(wh == 0 || pad_token != nullptr || (gh % wh == 0 && gw % ww == 0), "et_window_attention: padding needs pad_token");
+        ET_CHECK_ARG(wh > 0 || rel_y == nullptr || gh * gw == N, "et_window_attention: rel-pos needs N == gh * gw");
+        // the statistics live at the END of the workspace (the front is the 16-bit paths' bias scratch)
+        const int64_t total = et_attn_workspace_bytes(B, N, gh, gw, wh, ww, heads, dh, 0, rel_y != nullptr);
+        const int64_t nw = wh > 0 ? ((gh + wh - 1) / wh) * ((gw + ww - 1) / ww) : 1;
+        const int64_t need = B * nw * heads * (wh > 0 ? wh * ww : N) * 2 * 4;
+        float* stats = reinterpret_cast<float*>(static_cast<char*>(workspace) + (total - need - 256) / 16 * 16);
+        int rc = et_generic_window_attention(qkv, pad_token, rel_y, rel_x, out, stats, (int)B, (int)N, (int)gh, (int)gw, (int)wh,
+                                             (int)ww, (int)heads, (int)dh, dtype, et_stream(stream));
+        if (rc) return rc;
+        ET_CHECK_LAUNCH("et_window_attention");
+        return ET_OK;
+    }
     ET_CHECK_ARG(et_aligned16(qkv) && et_aligned16(out) && et_aligned16(pad_token) && et_aligned16(workspace),
                  "et_window_attention: pointers must be 16-byte aligned");
     AttnArgs a = {};
@@ -939,23 +968,38 @@ int et_window_attention(const void* qkv, const void* pad_token, const void* rel_
     return ET_OK;
 }
 
-int et_global_attention(const void* qkv, const void* rel_y, const void* rel_x, int mode, const int64_t* idx,
-                           int64_t k, void* a_state, void* v_state, void* acc, void* out, float* row_stats,
-                           void* workspace, int64_t B, int64_t N, int64_t gh, int64_t gw, int64_t heads, int64_t dh,
-                           int dtype, void* stream) {
+int et_global_attention(const void* qkv, const void* kv_pooled, int64_t pool_h, int64_t pool_w, const void* rel_y,
+                        const void* rel_x, int mode, const int64_t* idx, const int32_t* count, int64_t k, void* a_state,
+                        void* v_state, void* acc, void* out, float* row_stats, void* workspace, int64_t B, int64_t N,
+                        int64_t gh, int64_t gw, int64_t heads, int64_t dh, int dtype, int state_dtype, void* stream) {
     ET_CHECK_ARG(qkv && out && row_stats, "et_global_attention: null pointer");
-    ET_CHECK_ARG(dtype == ET_BF16 || dtype == ET_F16, "et_global_attention: bf16 / fp16 only (dtype=%d)", dtype);
+    ET_CHECK_ARG(dtype == ET_BF16 || dtype == ET_F16 || dtype == ET_F32, "et_global_attention: bad dtype %d", dtype);
+    ET_CHECK_ARG(state_dtype == ET_BF16 || state_dtype == ET_F16 || state_dtype == ET_F32, "et_global_attention: bad state dtype %d", state_dtype);
     ET_CHECK_ARG(mode == ET_ATTN_DENSE || mode == ET_ATTN_FIRST || mode == ET_ATTN_DELTA, "et_global_attention: bad mode");
     ET_CHECK_ARG((rel_y == nullptr) == (rel_x == nullptr), "et_global_attention: rel_y / rel_x both or neither");
     ET_CHECK_ARG(rel_y == nullptr || gh * gw == N, "et_global_attention: rel-pos needs N == gh * gw");
     ET_CHECK_ARG(mode == ET_ATTN_DENSE || (a_state && v_state && acc), "et_global_attention: state pointers required");
     ET_CHECK_ARG(mode != ET_ATTN_DELTA || (idx != nullptr && k >= 0 && k <= N), "et_global_attention: DELTA needs idx, k <= N");
     ET_CHECK_ARG((mode != ET_ATTN_DELTA && rel_y == nullptr) || workspace != nullptr, "et_global_attention: workspace required");
+    ET_CHECK_ARG(count == nullptr || mode == ET_ATTN_DELTA, "et_global_attention: count applies to DELTA mode");
+    if (kv_pooled != nullptr)
+        ET_CHECK_ARG(pool_h > 0 && pool_w > 0 && gh * gw == N && gh % pool_h == 0 && gw % pool_w == 0,
+                     "et_global_attention: pooled keys need a %lld x %lld grid divisible by the pool size", (long long)gh, (long long)gw);
+    if (dtype == ET_F32 || state_dtype != dtype || kv_pooled != nullptr) {
+        // general-precision path (et_generic.cu): fp32 models, matmul_2_cast != model dtype, pooled keys / values
+        ET_CHECK_ARG(dh <= 64, "et_global_attention (general path): head dim %lld > 64", (long long)dh);
+        int rc = et_generic_global_attention(qkv, kv_pooled, (int)pool_h, (int)pool_w, rel_y, rel_x, mode, idx, count, (int)k, a_state,
+                                             v_state, acc, out, row_stats, workspace, (int)B, (int)N, (int)gh, (int)gw, (int)heads,
+                                             (int)dh, dtype, state_dtype, et_stream(stream));
+        if (rc) return rc;
+        ET_CHECK_LAUNCH("et_global_attention");
+        return ET_OK;
+    }
     AttnArgs a = {};
     a.qkv = qkv; a.out = out; a.B = (int)B; a.N = (int)N; a.NP = (int)((N + 7) / 8 * 8); a.gh = (int)gh; a.gw = (int)gw;
     a.H = (int)heads;
     a.windowed = 0; a.nwx = a.nwy = 1; a.Wn = (int)N; a.rscale = 1.0f / sqrtf((float)dh);
-    a.idx = reinterpret_cast<const long long*>(idx); a.k = (int)(mode == ET_ATTN_DELTA ? k : 0); a.mode = mode;
+    a.idx = reinterpret_cast<const long long*>(idx); a.count = count; a.k = (int)(mode == ET_ATTN_DELTA ? k : 0); a.mode = mode;
     a.a_state = a_state; a.acc = acc; a.stats = row_stats;
     if (rel_y == nullptr) { a.gh = 0; a.gw = 0; }
     int rc = ET_OK;

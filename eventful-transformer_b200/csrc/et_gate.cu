@@ -689,7 +689,7 @@ int grid_for(long long work_items, int threads) {
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
-int et_version(void) { return 100; }
+int et_version(void) { return 200; }
 
 long long et_launch_count(void) { return g_et_launches; }
 

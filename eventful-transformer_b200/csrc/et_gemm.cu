@@ -15,6 +15,10 @@
 // n_feat % 8 == 0 are accepted.
 #include "et_tcgen05.cuh"
 
+int et_generic_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bias, int64_t n_feat, int act, void* out,
+                      int64_t ld_out, const int64_t* idx, const int32_t* count, int64_t k, int64_t n_out_rows,
+                      cudaStream_t stream);
+
 namespace {
 
 constexpr int BLOCK_M = 128;
@@ -108,6 +112,13 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const int n0 = blockIdx.x * BLOCK_N;
     const int m0 = blockIdx.y * (BLOCK_M * MH);
     const int num_k_blocks = (args.K + BLOCK_K - 1) / BLOCK_K;
+    if (args.count != nullptr) {
+        // device-side row count (threshold policy): a tile made only of rows beyond it has nothing to compute or store
+        et_pdl_wait();
+        const int mlast = min(args.M, m0 + BLOCK_M * MH) - 1;
+        const int b0 = m0 / args.k;
+        if (mlast / args.k == b0 && m0 - b0 * args.k >= args.count[b0]) return;
+    }
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -644,8 +655,19 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
               int64_t ld_out, const int64_t* idx, const int32_t* count, int64_t k, int64_t n_out_rows, int dtype,
               void* stream) {
     ET_CHECK_ARG(A && W && out, "et_linear: null pointer");
-    ET_CHECK_ARG(dtype == ET_BF16 || dtype == ET_F16,
-                 "et_linear: the tcgen05 path computes in bf16/fp16 with fp32 accumulation (dtype=%d)", dtype);
+    if (dtype == ET_F32) {  // fp32 models: CUDA-core SGEMM with the same epilogue (et_generic.cu)
+        ET_CHECK_ARG(M >= 0 && K > 0 && n_feat > 0 && M < (1LL << 31), "et_linear: bad shape");
+        ET_CHECK_ARG(et_aligned16(A) && et_aligned16(W), "et_linear: pointers must be 16-byte aligned");
+        ET_CHECK_ARG(act == ET_ACT_NONE || act == ET_ACT_GELU, "et_linear: unknown activation %d", act);
+        if (idx != nullptr) ET_CHECK_ARG(k > 0 && M % k == 0 && n_out_rows > 0, "et_linear: scatter needs k | M and n_out_rows");
+        ET_CHECK_ARG(count == nullptr || idx != nullptr, "et_linear: count needs idx");
+        if (M == 0) return ET_OK;
+        int rc32 = et_generic_linear(A, M, K, W, bias, n_feat, act, out, ld_out, idx, count, k, n_out_rows, et_stream(stream));
+        if (rc32) return rc32;
+        ET_CHECK_LAUNCH("et_linear");
+        return ET_OK;
+    }
+    ET_CHECK_ARG(dtype == ET_BF16 || dtype == ET_F16, "et_linear: unknown dtype %d", dtype);
     ET_CHECK_ARG(M >= 0 && K > 0 && n_feat > 0 && M < (1LL << 31) && K % 8 == 0 && n_feat % 8 == 0 && ld_out % 8 == 0,
                  "et_linear: need K, n_feat, ld_out multiples of 8 (M=%lld K=%lld n_feat=%lld ld_out=%lld)",
                  (long long)M, (long long)K, (long long)n_feat, (long long)ld_out);
@@ -691,7 +713,7 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
         const int pbn = g_force_block_n == 128 || g_force_block_n == 192 ? g_force_block_n : 256;
         const long long ptiles = mt * ((n_feat + pbn - 1) / pbn);
         const bool long_k = K >= 2048;  // long-K layers do better with 256-row tiles (below)
-        const bool persist = g_force_persist ? g_force_persist == 1 : (ptiles >= 2 * sms && g_force_mh == 0 && !long_k);
+        const bool persist = g_force_persist ? g_force_persist == 1 : (ptiles >= 2 * sms && g_force_mh == 0 && !long_k && count == nullptr);
         if (persist) {
             switch (pbn) {
                 case 128: rc = launch_persistent<128, 5>(A, W, a, s); break;

@@ -1,64 +1,97 @@
-// Generic strided batched matmul for the stand-alone MatmulBuffer / MatmulDeltaAccumulator modules
-// (modules.py:204-299 used outside the fused block path).  Plain shared-memory tiling on CUDA cores,
-// fp32 accumulate; the fused attention kernels in et_attn.cu are the performance path.
+// Generic strided batched matmul C = alpha * A @ B (+ C) for the stand-alone MatmulBuffer / MatmulDeltaAccumulator /
+// CountedMatmul modules (modules.py:204-299, counting.py:165-175 used outside the fused block path; operands are
+// arbitrary strided views such as the q / k^T views of a QKV buffer).  Register-tiled on the CUDA cores: 64 x 64 output
+// tile per CTA, 4 x 4 per thread, fp32 accumulate; the fused attention kernels are the performance path.
 #include "et_common.cuh"
 
 namespace {
 
-constexpr int TILE = 16;
+constexpr int BT = 64, BKK = 16, BTHREADS = 256, BLD = BT + 4;
 
 struct BmmArgs {
     const void* A;
     const void* B;
     void* C;
     long long M, N, K;
-    long long sab, sam, sak, sbb, sbk, sbn, scb, scm, scn;
+    long long sab, sai, sam, sak, sbb, sbi, sbk, sbn, scb, sci, scm, scn;  // outer-batch, inner-batch, row, column strides
+    int inner;
     int accumulate;
+    float alpha;
 };
 
 template <typename T>
-__global__ void __launch_bounds__(TILE * TILE) bmm_kernel(const BmmArgs a) {
+__global__ void __launch_bounds__(BTHREADS) bmm_kernel(const BmmArgs a) {
     et_pdl_prologue();
-    __shared__ float As[TILE][TILE + 1];
-    __shared__ float Bs[TILE][TILE + 1];
-    const T* A = static_cast<const T*>(a.A) + (long long)blockIdx.z * a.sab;
-    const T* B = static_cast<const T*>(a.B) + (long long)blockIdx.z * a.sbb;
-    T* C = static_cast<T*>(a.C) + (long long)blockIdx.z * a.scb;
-    const int tx = threadIdx.x % TILE, ty = threadIdx.x / TILE;
-    const long long m = (long long)blockIdx.y * TILE + ty, n = (long long)blockIdx.x * TILE + tx;
-    float acc = 0.f;
-    for (long long k0 = 0; k0 < a.K; k0 += TILE) {
-        As[ty][tx] = (m < a.M && k0 + tx < a.K) ? ElemTraits<T>::to_float(A[m * a.sam + (k0 + tx) * a.sak]) : 0.f;
-        Bs[ty][tx] = (k0 + ty < a.K && n < a.N) ? ElemTraits<T>::to_float(B[(k0 + ty) * a.sbk + n * a.sbn]) : 0.f;
+    __shared__ __align__(16) float As[BKK][BLD];  // As[k][m]
+    __shared__ __align__(16) float Bs[BKK][BLD];  // Bs[k][n]
+    const long long bo = blockIdx.z / a.inner, bi = blockIdx.z - bo * a.inner;
+    const T* A = static_cast<const T*>(a.A) + bo * a.sab + bi * a.sai;
+    const T* B = static_cast<const T*>(a.B) + bo * a.sbb + bi * a.sbi;
+    T* C = static_cast<T*>(a.C) + bo * a.scb + bi * a.sci;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const long long m0 = (long long)blockIdx.y * BT, n0 = (long long)blockIdx.x * BT;
+    // loader index order follows the unit-stride axis of each operand so that global reads coalesce
+    const bool a_k_fast = a.sak == 1, b_n_fast = a.sbn == 1;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (long long k0 = 0; k0 < a.K; k0 += BKK) {
+        for (int i = tid; i < BT * BKK; i += BTHREADS) {
+            const int m = a_k_fast ? i / BKK : i % BT, kk = a_k_fast ? i % BKK : i / BT;
+            As[kk][m] = (m0 + m < a.M && k0 + kk < a.K) ? ElemTraits<T>::to_float(A[(m0 + m) * a.sam + (k0 + kk) * a.sak]) : 0.f;
+            const int n = b_n_fast ? i % BT : i / BKK, kb = b_n_fast ? i / BT : i % BKK;
+            Bs[kb][n] = (n0 + n < a.N && k0 + kb < a.K) ? ElemTraits<T>::to_float(B[(k0 + kb) * a.sbk + (n0 + n) * a.sbn]) : 0.f;
+        }
         __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < TILE; ++kk) acc = fmaf(As[ty][kk], Bs[kk][tx], acc);
+        for (int kk = 0; kk < BKK; ++kk) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        }
         __syncthreads();
     }
-    if (m < a.M && n < a.N) {
-        T* c = C + m * a.scm + n * a.scn;
-        // `product += matmul(...)`: the matmul result is rounded to dtype before the in-place add (modules.py:293)
-        float v = round_to<T>(acc);
-        if (a.accumulate) v += ElemTraits<T>::to_float(*c);
-        *c = ElemTraits<T>::from_float(v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long n = n0 + tx * 4 + j;
+            if (n >= a.N) continue;
+            T* c = C + m * a.scm + n * a.scn;
+            // `product += matmul(...)`: the matmul result is rounded to dtype before the in-place add (modules.py:293)
+            float v = round_to<T>(acc[i][j] * a.alpha);
+            if (a.accumulate) v += ElemTraits<T>::to_float(*c);
+            *c = ElemTraits<T>::from_float(v);
+        }
     }
 }
 
 }  // namespace
 
-extern "C" int et_bmm(const void* A, const void* Bm, void* C, int64_t batch, int64_t M, int64_t N, int64_t K, int64_t sab,
-                      int64_t sam, int64_t sak, int64_t sbb, int64_t sbk, int64_t sbn, int64_t scb, int64_t scm,
-                      int64_t scn, int accumulate, int dtype, void* stream) {
-    ET_CHECK_ARG(A && Bm && C, "et_bmm: null pointer");
-    ET_CHECK_ARG(batch >= 0 && M >= 0 && N >= 0 && K >= 0 && batch <= 65535, "et_bmm: bad shape");
+extern "C" int et_bmm(const void* A, const void* Bm, void* C, int64_t batch_outer, int64_t batch_inner, int64_t M, int64_t N,
+                      int64_t K, const int64_t* strides_a, const int64_t* strides_b, const int64_t* strides_c, int accumulate,
+                      float alpha, int dtype, void* stream) {
+    ET_CHECK_ARG(A && Bm && C && strides_a && strides_b && strides_c, "et_bmm: null pointer");
+    const int64_t batch = batch_outer * batch_inner;
+    ET_CHECK_ARG(batch_outer >= 0 && batch_inner >= 0 && M >= 0 && N >= 0 && K >= 0 && batch <= 65535, "et_bmm: bad shape");
     if (batch == 0 || M == 0 || N == 0) return ET_OK;
     BmmArgs a;
-    a.A = A; a.B = Bm; a.C = C; a.M = M; a.N = N; a.K = K;
-    a.sab = sab; a.sam = sam; a.sak = sak; a.sbb = sbb; a.sbk = sbk; a.sbn = sbn; a.scb = scb; a.scm = scm; a.scn = scn;
-    a.accumulate = accumulate;
-    const dim3 grid((unsigned)((N + TILE - 1) / TILE), (unsigned)((M + TILE - 1) / TILE), (unsigned)batch);
+    a.A = A; a.B = Bm; a.C = C; a.M = M; a.N = N; a.K = K; a.inner = (int)batch_inner;
+    a.sab = strides_a[0]; a.sai = strides_a[1]; a.sam = strides_a[2]; a.sak = strides_a[3];
+    a.sbb = strides_b[0]; a.sbi = strides_b[1]; a.sbk = strides_b[2]; a.sbn = strides_b[3];
+    a.scb = strides_c[0]; a.sci = strides_c[1]; a.scm = strides_c[2]; a.scn = strides_c[3];
+    a.accumulate = accumulate; a.alpha = alpha;
+    const dim3 grid((unsigned)((N + BT - 1) / BT), (unsigned)((M + BT - 1) / BT), (unsigned)batch);
     ET_CHECK_ARG(grid.y <= 65535, "et_bmm: M too large");
-    ET_DISPATCH_DTYPE(dtype, T, { et_launch(bmm_kernel<T>, dim3(grid), dim3(TILE * TILE), 0, et_stream(stream), a); });
+    ET_DISPATCH_DTYPE(dtype, T, { et_launch(bmm_kernel<T>, dim3(grid), dim3(BTHREADS), 0, et_stream(stream), a); });
     ET_COUNT_LAUNCH(1);
     ET_CHECK_LAUNCH("et_bmm");
     return ET_OK;

@@ -47,8 +47,14 @@ def backbone_kwargs(cfg, input_size, block_class="EventfulBlock", windowed_class
     )
     if cfg.get("window_indices"):
         kw["windowed_class"] = windowed_class
+        # the reference's configs switch both variants off on windowed blocks (configs/*/vitdet_vid/_spatial.yml, _half.yml)
+        overrides = {}
         if matmul_2_cast is not None:
-            kw["windowed_overrides"] = dict(matmul_2_cast=None)
+            overrides["matmul_2_cast"] = None
+        if pool_size is not None:
+            overrides["pool_size"] = None
+        if overrides:
+            kw["windowed_overrides"] = overrides
     return kw
 
 

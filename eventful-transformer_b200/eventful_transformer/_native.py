@@ -47,10 +47,14 @@ _SIGNATURES = {
     "et_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                     c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "et_attn_workspace_bytes": (c_int64, [c_int64] * 9 + [c_int]),
-    "et_global_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
-                                    c_int64, c_int64, c_int, c_void_p]),
-    "et_bmm": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int64] * 13 + [c_int, c_int, c_void_p]),
+    "et_global_attention": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                    c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "et_pool_kv": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "et_pool_index": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                              c_void_p, c_void_p]),
+    "et_bmm": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int64] * 5 + [ctypes.POINTER(c_int64)] * 3
+               + [c_int, c_float, c_int, c_void_p]),
 }
 
 _lib = None
@@ -149,12 +153,15 @@ def _ticket(device, rows):
 # ----------------------------------------------------------------------------
 # op wrappers (torch tensors in, torch tensors out)
 # ----------------------------------------------------------------------------
-def gate_select(xa, p=None, xb=None, want_sum=False, ln=None, eps=1e-6, k=None, threshold=None, ticket=None):
+def gate_select(xa, p=None, xb=None, want_sum=False, ln=None, eps=1e-6, k=None, threshold=None, ticket=None,
+                device_count=False):
     """
     Fused [add] -> [LayerNorm] -> delta norm -> selection.  xa: (..., N, D).
     Returns (index (..., k) int64, xsum or None).  With `threshold` the result is
     (index (..., n), xsum) after ONE device->host read of the count, as the
-    reference's nonzero() does (policies.py:27-28).
+    reference's nonzero() does (policies.py:27-28) -- or, with device_count=True,
+    (index padded to (..., N), xsum, count (rows,) int32 on the device) with no host
+    synchronisation at all (CUDA-graph capturable; consumers take the count pointer).
     """
     require_device(xa)
     _dense(xa, "gate input")
@@ -187,13 +194,16 @@ def gate_select(xa, p=None, xb=None, want_sum=False, ln=None, eps=1e-6, k=None, 
                                 dtype_code(xa), mode, kk, thr, _p(norm), _p(idx), _p(count), _p(ticket), _stream()),
            "et_gate_select")
     if threshold is not None:
+        if device_count:
+            return idx, xsum, count
         found = int(count[0].item())  # host sync, like nonzero()
         idx = idx[..., :found]
     return idx, xsum
 
 
-def gate_gather(x, idx, p=None, ln=None, eps=1e-6, ln_after=False, want_delta=False, full_replace=False):
-    """c~ = LN?(x)[idx]; optional e~ = c~ - p[idx]; p[idx] = c~.  x: (..., N, D), idx: (..., k)."""
+def gate_gather(x, idx, p=None, ln=None, eps=1e-6, ln_after=False, want_delta=False, full_replace=False, count=None):
+    """c~ = LN?(x)[idx]; optional e~ = c~ - p[idx]; p[idx] = c~.  x: (..., N, D), idx: (..., k).
+    `count` (rows,) int32 on the device: only the first count[r] indices of each row are valid."""
     require_device(x)
     _dense(x, "gate input")
     _dense(idx, "index")
@@ -211,7 +221,7 @@ def gate_gather(x, idx, p=None, ln=None, eps=1e-6, ln_after=False, want_delta=Fa
     ln_w, ln_b = (None, None) if ln is None else ln
     if k == 0 and not full_replace:
         return c_tilde, e_tilde
-    _check(lib().et_gate_gather(_p(x), _p(ln_w), _p(ln_b), float(eps), int(ln_after), _p(p), _p(idx), None, rows, n,
+    _check(lib().et_gate_gather(_p(x), _p(ln_w), _p(ln_b), float(eps), int(ln_after), _p(p), _p(idx), _p(count), rows, n,
                                 d, k, dtype_code(x), _p(c_tilde), _p(e_tilde), int(full_replace), _stream()),
            "et_gate_gather")
     return c_tilde, e_tilde
@@ -264,7 +274,7 @@ def sub(a, b):
     return out
 
 
-def linear(x, weight, bias, act=ACT_NONE, out=None, idx=None, n_out_rows=0):
+def linear(x, weight, bias, act=ACT_NONE, out=None, idx=None, n_out_rows=0, count=None):
     """
     y = act(x @ W^T + b) on tcgen05.  x: (..., K).  With `idx` (B, k) and `out` (B, N, F) the rows
     are scattered into the TokenBuffer: out[b, idx[b, j]] = y[b, j].
@@ -283,8 +293,10 @@ def linear(x, weight, bias, act=ACT_NONE, out=None, idx=None, n_out_rows=0):
         kk, rows_out = idx.shape[-1], out.shape[-2]
         if kk == 0:
             return out
-    _check(lib().et_linear(_p(x), m, k_dim, _p(weight), _p(bias), f, int(act), _p(out), out.shape[-1], _p(idx), None,
-                           kk, rows_out, dtype_code(x), _stream()), "et_linear")
+    if weight.dtype != x.dtype or (bias is not None and bias.dtype != x.dtype):
+        raise TypeError(f"eventful_b200.linear: input is {x.dtype}, weight {weight.dtype}; cast the model or the input")
+    _check(lib().et_linear(_p(x), m, k_dim, _p(weight), _p(bias), f, int(act), _p(out), out.shape[-1], _p(idx),
+                           _p(count), kk, rows_out, dtype_code(x), _stream()), "et_linear")
     return out
 
 
@@ -303,15 +315,21 @@ def window_attention(qkv, heads, grid, window, pad_token=None, rel=None):
     gh, gw = grid
     wh, ww = window if window is not None else (0, 0)
     out = torch.empty((b, n, d), dtype=qkv.dtype, device=qkv.device)
-    ws = attn_workspace(b, n, gh, gw, wh, ww, heads, dh, 0, rel is not None, qkv.device) if rel is not None else None
+    need_ws = rel is not None or qkv.dtype == torch.float32
+    ws = attn_workspace(b, n, gh, gw, wh, ww, heads, dh, 0, rel is not None, qkv.device) if need_ws else None
     rel_y, rel_x = (None, None) if rel is None else rel
     _check(lib().et_window_attention(_p(qkv), _p(pad_token), _p(rel_y), _p(rel_x), _p(out), _p(ws), b, n, gh, gw, wh,
                                      ww, heads, dh, dtype_code(qkv), _stream()), "et_window_attention")
     return out
 
 
-def global_attention(qkv, heads, grid, mode, rel=None, idx=None, a_state=None, v_state=None, acc=None, stats=None):
-    """Global attention over the QKV buffer in DENSE / FIRST / DELTA mode -> fresh (B, N, D) output."""
+def global_attention(qkv, heads, grid, mode, rel=None, idx=None, a_state=None, v_state=None, acc=None, stats=None,
+                     count=None, kv_pooled=None, pool=None, state_dtype=None):
+    """
+    Global attention over the QKV buffer in DENSE / FIRST / DELTA mode -> fresh (B, N, D) output (model dtype).
+    kv_pooled / pool: pooled keys and values (pool_kv) and the pooling ratio; count: device-side number of valid
+    entries of idx per batch entry; state_dtype: element type of a_state / v_state / acc (matmul_2_cast).
+    """
     require_device(qkv)
     _dense(qkv, "qkv")
     b, n, d3 = qkv.shape
@@ -320,32 +338,77 @@ def global_attention(qkv, heads, grid, mode, rel=None, idx=None, a_state=None, v
     gh, gw = grid
     k = 0 if idx is None else idx.shape[-1]
     if mode == ATTN_DELTA and k == 0:
-        return acc.clone()  # nothing selected: the accumulator is unchanged
+        return acc.to(qkv.dtype)  # nothing selected: the accumulator is unchanged (a copy, never the state itself)
     out = torch.empty((b, n, d), dtype=qkv.dtype, device=qkv.device)
     if stats is None:
         stats = torch.empty((b, heads, n, 2), dtype=torch.float32, device=qkv.device)
-    ws = attn_workspace(b, n, gh, gw, 0, 0, heads, dh, k, rel is not None, qkv.device)
+    sdt = _DTYPES[qkv.dtype if state_dtype is None else state_dtype]
+    ws = attn_workspace(b, n, gh, gw, 0, 0, heads, dh, 2 * k if sdt == ET_F32 else k, rel is not None, qkv.device)
     rel_y, rel_x = (None, None) if rel is None else rel
-    _check(lib().et_global_attention(_p(qkv), _p(rel_y), _p(rel_x), int(mode), _p(idx), k, _p(a_state), _p(v_state),
-                                     _p(acc), _p(out), _p(stats), _p(ws), b, n, gh, gw, heads, dh, dtype_code(qkv),
-                                     _stream()), "et_global_attention")
+    ph, pw = (1, 1) if pool is None else pool
+    for t, name in ((idx, "index"), (kv_pooled, "pooled keys"), (a_state, "A-gate state"), (v_state, "v-gate state"),
+                    (acc, "accumulator")):
+        if t is not None:
+            _dense(t, name)
+    _check(lib().et_global_attention(_p(qkv), _p(kv_pooled), ph, pw, _p(rel_y), _p(rel_x), int(mode), _p(idx), _p(count), k,
+                                     _p(a_state), _p(v_state), _p(acc), _p(out), _p(stats), _p(ws), b, n, gh, gw, heads,
+                                     dh, dtype_code(qkv), sdt, _stream()), "et_global_attention")
     return out
 
 
-def bmm(a, b, out=None, accumulate=False):
-    """Strided batched matmul on (..., M, K) x (..., K, N); views welcome (element strides are passed)."""
+def pool_kv(qkv, grid, pool):
+    """(B, gh*gw, 3D) -> (B, Nk, 2D) = [k | v] averaged over pool cells (Block._pool_tokens, blocks.py:303-326)."""
+    require_device(qkv)
+    _dense(qkv, "qkv")
+    b, n, d3 = qkv.shape
+    d = d3 // 3
+    gh, gw = grid
+    if gh * gw != n:
+        raise ValueError("eventful_b200.pool_kv: K/V pooling needs a token grid without extra tokens")
+    out = torch.empty((b, (gh // pool[0]) * (gw // pool[1]), 2 * d), dtype=qkv.dtype, device=qkv.device)
+    _check(lib().et_pool_kv(_p(qkv), _p(out), b, gh, gw, d, pool[0], pool[1], dtype_code(qkv), _stream()), "et_pool_kv")
+    return out
+
+
+def pool_index(idx, count, grid, pool):
+    """Token indices (B, k) [+ device count] -> (pooled-cell ids (B, k) ascending unique, count (B,) int32)."""
+    require_device(idx)
+    _dense(idx, "index")
+    b, k = idx.shape
+    out = torch.empty_like(idx)
+    out_count = torch.empty((b,), dtype=torch.int32, device=idx.device)
+    if k == 0:
+        return out, out_count.zero_()
+    _check(lib().et_pool_index(_p(idx), _p(count), b, k, grid[0], grid[1], pool[0], pool[1], _p(out), _p(out_count),
+                               _stream()), "et_pool_index")
+    return out, out_count
+
+
+def _batch2(t):
+    """(tensor, (outer, inner)) with exactly two leading batch dims, without copying when the layout allows it."""
+    if t.dim() == 2:
+        return t.unsqueeze(0).unsqueeze(0)
+    if t.dim() == 3:
+        return t.unsqueeze(0)
+    if t.dim() == 4:
+        return t
+    lead = t.shape[:-3]  # more than two batch dims: fold all but the last one (a view when possible, else a copy)
+    return t.reshape((-1,) + tuple(t.shape[-3:])) if len(lead) else t
+
+
+def bmm(a, b, out=None, accumulate=False, alpha=1.0):
+    """Batched matmul alpha * (..., M, K) x (..., K, N) -> (..., M, N); strided views welcome (element strides are
+    passed down, two batch levels natively)."""
     require_device(a)
+    if a.dtype != b.dtype or a.shape[:-2] != b.shape[:-2] or a.shape[-1] != b.shape[-2]:
+        raise ValueError(f"eventful_b200.bmm: operands do not match ({tuple(a.shape)} x {tuple(b.shape)})")
     m, kd, n = a.shape[-2], a.shape[-1], b.shape[-1]
-    lead = tuple(a.shape[:-2])
-    a3 = a.reshape((-1, m, kd)) if a.is_contiguous() else a.flatten(0, -3) if a.dim() > 3 else a
-    b3 = b.reshape((-1, kd, n)) if b.is_contiguous() else b.flatten(0, -3) if b.dim() > 3 else b
-    if a3.dim() == 2:
-        a3, b3 = a3.unsqueeze(0), b3.unsqueeze(0)
     if out is None:
-        out = torch.empty(lead + (m, n), dtype=a.dtype, device=a.device)
-    o3 = out.view((-1, m, n))
-    batch = o3.shape[0]
-    _check(lib().et_bmm(_p(a3), _p(b3), _p(o3), batch, m, n, kd, a3.stride(0), a3.stride(1), a3.stride(2),
-                        b3.stride(0), b3.stride(1), b3.stride(2), o3.stride(0), o3.stride(1), o3.stride(2),
-                        int(accumulate), dtype_code(a), _stream()), "et_bmm")
+        out = torch.empty(tuple(a.shape[:-2]) + (m, n), dtype=a.dtype, device=a.device)
+    a4, b4, o4 = _batch2(a), _batch2(b), _batch2(out)
+    if o4.data_ptr() != out.data_ptr():
+        raise ValueError("eventful_b200.bmm: the output must be viewable with two batch dims")
+    arr = lambda t: (c_int64 * 4)(*t.stride())  # noqa: E731
+    _check(lib().et_bmm(_p(a4), _p(b4), _p(o4), o4.shape[0], o4.shape[1], m, n, kd, arr(a4), arr(b4), arr(o4),
+                        int(accumulate), float(alpha), dtype_code(a), _stream()), "et_bmm")
     return out

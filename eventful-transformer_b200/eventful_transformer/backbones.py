@@ -82,9 +82,10 @@ class ViTBackbone(ExtendedModule):
         key = []
         for gate in self.modules_of_type((TokenGate, TokenDeltaGate, SimpleSTGTGate)):
             spec = _policy_spec(gate.policy, n_tokens) if gate.policy is not None else None
-            if gate.policy is not None and (spec is None or "threshold" in spec):
-                return None  # data-dependent shapes / user code: not capturable
-            key.append(None if spec is None else spec["k"])
+            if gate.policy is not None and spec is None:
+                return None  # user code: not capturable
+            # top-k: fixed shapes; threshold: padded index + device-side count, also a fixed launch sequence
+            key.append(None if spec is None else tuple(sorted(spec.items())))
         return tuple(key)
 
     def _graphable(self, x):

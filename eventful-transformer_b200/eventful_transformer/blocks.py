@@ -13,8 +13,14 @@ and for attention
 A block hands its output to the next one as an un-summed pair (branch, skip) so that the residual
 add is fused into the next gate's load; Block.forward(x) is still the ordinary stand-alone call.
 
-Not implemented yet (reference features outside the round-1 scope): adaptive
-token sampling (ats_fraction), K/V pooling (pool_size), drop-path in training mode.
+Selections travel through a block as (index, count): `count` is None for top-k policies (all k
+entries valid) or a device-side int32 tensor (threshold policy, pooled unique indices) that every
+consumer kernel takes as a pointer -- no host synchronisation, so those frames are CUDA-graph
+capturable too.
+
+Variants: K/V pooling (pool_size; global blocks), matmul_2_cast different from
+the model dtype and fp32 models run on the general-precision kernels (csrc/et_generic.cu).
+Not implemented: adaptive token sampling (ats_fraction), drop-path in training mode.
 """
 
 from math import prod, sqrt
@@ -70,9 +76,11 @@ class Block(ExtendedModule):
         self.ats_fraction = ats_fraction
         self.last_ats_indices = None
         self.matmul_2_cast = matmul_2_cast
-        if pool_size is not None:
-            raise NotImplementedError("eventful_b200: K/V pooling (pool_size) is not implemented yet")
-        self.pool_size = None
+        self.pool_size = None if pool_size is None else numeric_tuple(pool_size, length=2)
+        if self.pool_size is not None and window_size is not None:
+            # every shipped config pools the global blocks only (configs/*/vitdet_vid/_spatial.yml: windowed_overrides
+            # pool_size null)
+            raise NotImplementedError("eventful_b200: K/V pooling inside windowed attention is not implemented")
         if window_size is None:
             self.window_size = None
             attention_size = self.input_size
@@ -89,7 +97,7 @@ class Block(ExtendedModule):
         self.drop_path = DropPath(drop_path_rate) if drop_path_rate > 0.0 else nn.Identity()
         if relative_embedding_size is not None:
             self.relative_position = RelativePositionEmbedding(
-                attention_size, tuple(relative_embedding_size), dim // heads, pool_size=None)
+                attention_size, tuple(relative_embedding_size), dim // heads, pool_size=self.pool_size)
         else:
             self.relative_position = None
         self.matmul = CountedMatmul()
@@ -124,11 +132,13 @@ class Block(ExtendedModule):
             raise RuntimeError("eventful_b200 is an inference path: its kernels record no autograd graph, so gradients "
                                "would silently be missing. Run under torch.inference_mode() / torch.no_grad() "
                                "(as scripts/time/vitdet_vid.py:28 of the reference does) or freeze the parameters.")
-        cast = self.matmul_2_cast
-        if cast is not None and getattr(torch, cast) != x.dtype:
-            raise NotImplementedError(
-                f"eventful_b200: matmul_2_cast='{cast}' on a {x.dtype} model is not implemented; the attention "
-                "kernels run in the model dtype (use model.to(torch.bfloat16) with matmul_2_cast None/'bfloat16')")
+        if self.window_size is not None and self._state_dtype(x.dtype) != x.dtype:
+            raise NotImplementedError("eventful_b200: matmul_2_cast different from the model dtype is implemented for "
+                                      "global attention only (the reference's configs set it to null on windowed blocks)")
+
+    def _state_dtype(self, model_dtype):
+        """Element type of a, v, the v-gate / A-gate state and the accumulator (_cast_matmul_2, blocks.py:183-189)."""
+        return model_dtype if self.matmul_2_cast is None else getattr(torch, self.matmul_2_cast)
 
     @staticmethod
     def _ln_params(ln):
@@ -175,19 +185,28 @@ class Block(ExtendedModule):
                 if rel is not None:
                     self.relative_position.count_fused(b * n_win * self.heads, w2, w2)
             return out
-        if n <= _SMALL_ATTENTION:
+        sdt = self._state_dtype(qkv.dtype)
+        n_keys = n
+        if self.pool_size is not None or sdt != qkv.dtype:
+            kvp = None
+            if self.pool_size is not None:
+                kvp = native.pool_kv(qkv, self.input_size, self.pool_size)
+                n_keys = kvp.shape[1]
+            out = native.global_attention(qkv, self.heads, self.input_size, native.ATTN_DENSE, rel=rel, kv_pooled=kvp,
+                                          pool=self.pool_size, state_dtype=sdt)
+        elif n <= _SMALL_ATTENTION:
             out = native.window_attention(qkv, self.heads, self.input_size, None, rel=rel)
         else:
             out = native.global_attention(qkv, self.heads, self.input_size, native.ATTN_DENSE, rel=rel)
         if self.count_mode:
-            self.matmul.counts["matmul_flops"] += 2 * b * self.heads * n * n * dh
+            self.matmul.counts["matmul_flops"] += 2 * b * self.heads * n * n_keys * dh
             if rel is not None:
-                self.relative_position.count_fused(b * self.heads, n, n)
+                self.relative_position.count_fused(b * self.heads, n, n_keys)
         return out
 
-    def _mlp(self, c, out=None, idx=None):
-        h = self.mlp_1(c, act=native.ACT_GELU)
-        return self.mlp_2(h, out=out, idx=idx)
+    def _mlp(self, c, out=None, idx=None, count=None, rows=None):
+        h = self.mlp_1(c, act=native.ACT_GELU, rows=rows)
+        return self.mlp_2(h, out=out, idx=idx, count=count, rows=rows)
 
     # Pair protocol: input is xa (+ xb), output is (branch, skip) whose sum is the block output.
     def _forward_pair(self, xa, xb):
@@ -220,31 +239,43 @@ class EventfulTokenwiseBlock(Block):
     # ------------------------------------------------------------------ gate site
     def _gate_site(self, gate, xa, xb, ln):
         """
-        One gate site on an incremental frame.  Returns (x, c_tilde, index) where x = xa (+ xb) is the
-        site input (materialised only when there is a residual to add).
+        One gate site on an incremental frame.  Returns (x, c_tilde, index, count) where x = xa (+ xb) is the
+        site input (materialised only when there is a residual to add) and count is None (all entries of index
+        valid) or a device-side int32 tensor (threshold policy: index is padded to N, no host synchronisation).
         """
         ln_p = None if ln is None else self._ln_params(ln)
         pre, post = (None, ln_p) if self.gate_before_ln else (ln_p, None)
         if gate.count_mode:
             gate.counts["gate_flops"] += gate.p.numel()
         spec = _policy_spec(gate.policy, xa.shape[-2])
+        count = None
         if spec is not None:
             if "threshold" in spec:
                 assert xa.shape[0] == 1  # policies.py:25
-            index, xsum = native.gate_select(xa, p=gate.p, xb=xb, want_sum=True, ln=pre, eps=LN_EPS, **spec)
+                index, xsum, count = native.gate_select(xa, p=gate.p, xb=xb, want_sum=True, ln=pre, eps=LN_EPS,
+                                                        device_count=True, **spec)
+            else:
+                index, xsum = native.gate_select(xa, p=gate.p, xb=xb, want_sum=True, ln=pre, eps=LN_EPS, **spec)
             x = xsum if xb is not None else xa
         else:  # user-defined policy: materialise the error tensor and call it
             x = native.add(xa, xb) if xb is not None else xa
             c = x if pre is None else self._layer_norm_all(ln, x)
             index = gate.policy(native.sub(c, gate.p), dim=-1)
         index = index.contiguous()
-        gate.last_index = index  # selection trace (tests / visualisation); a reference, no copy
+        gate._last_sel = (index, count)  # selection trace (gate.last_index); references, no copy
         if post is not None:
             c_tilde, _ = native.gate_gather(x, index, p=gate.p, ln=post, eps=LN_EPS, ln_after=True,
-                                            full_replace=self.stgt)
+                                            full_replace=self.stgt, count=count)
         else:
-            c_tilde, _ = native.gate_gather(x, index, p=gate.p, ln=pre, eps=LN_EPS, full_replace=self.stgt)
-        return x, c_tilde, index
+            c_tilde, _ = native.gate_gather(x, index, p=gate.p, ln=pre, eps=LN_EPS, full_replace=self.stgt, count=count)
+        return x, c_tilde, index, count
+
+    def _rows_selected(self, index, count):
+        """Host-side number of selected rows, for the op counters only (reads the device count when there is one)."""
+        if not self.count_mode:
+            return None
+        per_entry = index.shape[-1] if count is None else int(count.max().item())
+        return per_entry * (index.numel() // max(1, index.shape[-1]))
 
     def _gate_first(self, gate, x, ln):
         """Frame 0 of a gate site: returns the dense site output and initialises gate.p."""
@@ -266,7 +297,7 @@ class EventfulTokenwiseBlock(Block):
     def _attention_first(self, qkv, index):
         return self._dense_attention(qkv)
 
-    def _attention_incremental(self, qkv, index):
+    def _attention_incremental(self, qkv, index, count=None):
         return self._dense_attention(qkv)
 
     # ------------------------------------------------------------------ pair protocol
@@ -280,15 +311,16 @@ class EventfulTokenwiseBlock(Block):
             return self._first_pair(xa, xb)
         n = xa.shape[-2]
         # gate-accumulator 1: LN -> gate -> QKV -> buffer
-        x, c1, index = self._gate_site(self.qkv_gate, xa, xb, self.input_layer_norm)
-        qkv = self.qkv(c1, out=self.qkv_accumulator.b, idx=index)
-        attn = self._attention_incremental(qkv, index)
+        x, c1, index, count = self._gate_site(self.qkv_gate, xa, xb, self.input_layer_norm)
+        qkv = self.qkv(c1, out=self.qkv_accumulator.b, idx=index, count=count, rows=self._rows_selected(index, count))
+        attn = self._attention_incremental(qkv, index, count)
         # gate-accumulator 2: gate -> projection -> buffer
-        _, c2, index2 = self._gate_site(self.projection_gate, attn, None, None)
-        proj = self.projection(c2, out=self.projection_accumulator.b, idx=index2)
+        _, c2, index2, count2 = self._gate_site(self.projection_gate, attn, None, None)
+        proj = self.projection(c2, out=self.projection_accumulator.b, idx=index2, count=count2,
+                               rows=self._rows_selected(index2, count2))
         # gate-accumulator 3: (+ skip) -> LN -> gate -> MLP -> buffer
-        x2, c3, index3 = self._gate_site(self.mlp_gate, proj, x, self.mlp_layer_norm)
-        branch = self._mlp(c3, out=self.mlp_accumulator.b, idx=index3)
+        x2, c3, index3, count3 = self._gate_site(self.mlp_gate, proj, x, self.mlp_layer_norm)
+        branch = self._mlp(c3, out=self.mlp_accumulator.b, idx=index3, count=count3, rows=self._rows_selected(index3, count3))
         self._count_adds(x2)
         assert n == x2.shape[-2]
         return branch, x2
@@ -310,51 +342,90 @@ class EventfulTokenwiseBlock(Block):
 class EventfulMatmul1Block(EventfulTokenwiseBlock):
     """
     Adds eventfulness to the query-key product (reference blocks.py:466-540).  The reference keeps the
-    N x N product as state and refreshes k rows and k columns; since that state always equals
-    (q / scale) k^T of the current QKV buffer, this implementation recomputes the logits tile by tile
-    on tensor cores instead of storing them, so the attention here is the dense global kernel.
+    N x Nk product as state and refreshes k rows and k columns; since that state always equals
+    (q / scale) k^T of the current QKV buffer, this implementation recomputes the logits tile by
+    tile inside the attention kernels instead of storing them.  `matmul_accumulator_1.product` is still
+    available: it is computed on demand from the block's current QKV buffer.
     """
 
     def __init__(self, **super_kwargs):
         super().__init__(**super_kwargs)
+        if self.pool_size is not None:  # _pool_index assumes divisibility (reference blocks.py:479-482)
+            assert all(s % p == 0 for s, p in zip(self.input_size, self.pool_size))
         assert self.window_size is None  # reference blocks.py:485
         self.matmul_accumulator_1 = MatmulBuffer()
+        self.matmul_accumulator_1._producer = self._matmul_1_product
 
-    def _count_matmul_1(self, qkv, k_sel):
+    # -- the state the reference stores, recomputed from the QKV buffer when somebody asks for it
+    def _matmul_1_product(self):
+        qkv = self.qkv_accumulator.b
+        if qkv is None:
+            return None
+        b, n, _ = qkv.shape
+        h, dh = self.heads, self.dim // self.heads
+        q = qkv[..., : self.dim].reshape(b, n, h, dh).permute(0, 2, 1, 3)
+        if self.pool_size is not None:
+            kv = native.pool_kv(qkv, self.input_size, self.pool_size)
+            keys = kv[..., : self.dim].reshape(b, kv.shape[1], h, dh).permute(0, 2, 3, 1)
+        else:
+            keys = qkv[..., self.dim: 2 * self.dim].reshape(b, n, h, dh).permute(0, 2, 3, 1)
+        return native.bmm(q, keys, alpha=1.0 / self.scale)
+
+    def _pooled(self, qkv, index, count):
+        """(pooled [k | v] tensor, pooled index, its device-side count) -- or (None, index, count) without pooling."""
+        if self.pool_size is None:
+            return None, index, count
+        kvp = native.pool_kv(qkv, self.input_size, self.pool_size)
+        if index is None:
+            return kvp, None, None
+        index_k, count_k = native.pool_index(index, count, self.input_size, self.pool_size)  # blocks.py:525-540
+        return kvp, index_k, count_k
+
+    def _count_matmul_1(self, qkv, n_keys, rows_q, cols_k):
+        """Counters of MatmulBuffer: full product (rows_q None) or the row + column refresh (modules.py:236-247)."""
         if self.count_mode:
             b, n, _ = qkv.shape
             dh = self.dim // self.heads
-            if k_sel is None:
-                self.matmul_accumulator_1.matmul.counts["matmul_flops"] += b * self.heads * n * n * dh
+            mm = self.matmul_accumulator_1.matmul.counts
+            if rows_q is None:
+                mm["matmul_flops"] += b * self.heads * n * n_keys * dh
             else:
-                self.matmul_accumulator_1.matmul.counts["matmul_flops"] += 2 * b * self.heads * n * k_sel * dh
+                mm["matmul_flops"] += b * self.heads * (rows_q * n_keys + n * cols_k) * dh
             if self.relative_position is not None:
-                self.relative_position.count_fused(b * self.heads, n, n)
+                self.relative_position.count_fused(b * self.heads, n, n_keys)
 
     def _global(self, qkv, mode, **kw):
-        return native.global_attention(qkv, self.heads, self.input_size, mode, rel=self._rel_tables(qkv.dtype), **kw)
+        return native.global_attention(qkv, self.heads, self.input_size, mode, rel=self._rel_tables(qkv.dtype),
+                                       pool=self.pool_size, state_dtype=self._state_dtype(qkv.dtype), **kw)
 
     def _attention_first(self, qkv, index):
         self.matmul_accumulator_1.first = False
         return self._attention_incremental(qkv, None)
 
-    def _attention_incremental(self, qkv, index):
+    def _attention_incremental(self, qkv, index, count=None):
         b, n, _ = qkv.shape
-        self._count_matmul_1(qkv, None if index is None else index.shape[-1])
+        kvp, index_k, count_k = self._pooled(qkv, index, count)
+        n_keys = n if kvp is None else kvp.shape[1]
         if self.count_mode:
-            self.matmul.counts["matmul_flops"] += b * self.heads * n * n * (self.dim // self.heads)
-        return self._global(qkv, native.ATTN_DENSE)
+            if index is None:
+                self._count_matmul_1(qkv, n_keys, None, None)
+            else:
+                self._count_matmul_1(qkv, n_keys, self._rows_selected(index, count) // b,
+                                     self._rows_selected(index_k, count_k) // b)
+            self.matmul.counts["matmul_flops"] += b * self.heads * n * n_keys * (self.dim // self.heads)
+        return self._global(qkv, native.ATTN_DENSE, kv_pooled=kvp)
 
 
 class EventfulBlock(EventfulMatmul1Block):
     """
     Also gates the attention-value product (reference blocks.py:543-575): v-gate and A-gate forced by
-    the QKV gate's index, MatmulDeltaAccumulator update -- one fused kernel pair here.
+    the (pooled) QKV gate index, MatmulDeltaAccumulator update -- one fused kernel pair here.
 
-    State (allocated at frame 0, exposed with the reference's logical shapes):
-        v_gate.p                      (B, H, N, dh)  view of a (B, N, D) tensor
-        matmul_gate.p                 (B, H, N, N)   view of the column-major (B, H, N, NP) A-state
-        matmul_accumulator_2.product  (B, H, N, dh)  view of a (B, N, D) tensor
+    State (allocated at frame 0 in the matmul_2_cast dtype, exposed with the reference's logical shapes;
+    Nk = N, or the pooled key count):
+        v_gate.p                      (B, H, Nk, dh)  view of a (B, Nk, D) tensor
+        matmul_gate.p                 (B, H, N, Nk)   view of the column-major (B, H, Nk, NP) A-state
+        matmul_accumulator_2.product  (B, H, N, dh)   view of a (B, N, D) tensor
     """
 
     def __init__(self, **super_kwargs):
@@ -373,33 +444,38 @@ class EventfulBlock(EventfulMatmul1Block):
         d, h = self.dim, self.heads
         dh = d // h
         n_pad = (n + 7) // 8 * 8
-        dev, dt = qkv.device, qkv.dtype
-        self._a_state = torch.zeros((b, h, n, n_pad), dtype=dt, device=dev)
-        self._v_state = torch.empty((b, n, d), dtype=dt, device=dev)
-        self._acc = torch.empty((b, n, d), dtype=dt, device=dev)
+        dev, sdt = qkv.device, self._state_dtype(qkv.dtype)
+        kvp, _, _ = self._pooled(qkv, None, None)
+        n_keys = n if kvp is None else kvp.shape[1]
+        self._a_state = torch.zeros((b, h, n_keys, n_pad), dtype=sdt, device=dev)
+        self._v_state = torch.empty((b, n_keys, d), dtype=sdt, device=dev)
+        self._acc = torch.empty((b, n, d), dtype=sdt, device=dev)
         self._stats = torch.empty((b, h, n, 2), dtype=torch.float32, device=dev)
         out = self._global(qkv, native.ATTN_FIRST, a_state=self._a_state, v_state=self._v_state, acc=self._acc,
-                           stats=self._stats)
+                           stats=self._stats, kv_pooled=kvp)
         self.matmul_accumulator_1.first = False
         self.v_gate.first = self.matmul_gate.first = self.matmul_accumulator_2.first = False
-        self.v_gate.p = self._v_state.view(b, n, h, dh).permute(0, 2, 1, 3)
+        self.v_gate.p = self._v_state.view(b, n_keys, h, dh).permute(0, 2, 1, 3)
         self.matmul_gate.p = self._a_state[..., :n].transpose(-1, -2)
         self.matmul_accumulator_2.product = self._acc.view(b, n, h, dh).permute(0, 2, 1, 3)
-        self._count_matmul_1(qkv, None)
+        self._count_matmul_1(qkv, n_keys, None, None)
         if self.count_mode:
-            self.matmul_accumulator_2.matmul.counts["matmul_flops"] += b * h * n * n * dh
+            self.matmul_accumulator_2.matmul.counts["matmul_flops"] += b * h * n * n_keys * dh
         return out
 
-    def _attention_incremental(self, qkv, index):
+    def _attention_incremental(self, qkv, index, count=None):
         b, n, _ = qkv.shape
         h = self.heads
         dh = self.dim // h
-        k_sel = index.shape[-1]
-        self._count_matmul_1(qkv, k_sel)
+        kvp, index_k, count_k = self._pooled(qkv, index, count)
+        n_keys = n if kvp is None else kvp.shape[1]
         if self.count_mode:
-            self.v_gate.counts["gate_flops"] += b * h * n * dh
-            self.matmul_gate.counts["gate_flops"] += b * h * n * n
-            self.matmul_accumulator_2.counts["accumulator_flops"] += b * (h * k_sel * dh + 2 * h * n * dh)
-            self.matmul_accumulator_2.matmul.counts["matmul_flops"] += 2 * b * h * n * k_sel * dh
-        return self._global(qkv, native.ATTN_DELTA, idx=index, a_state=self._a_state, v_state=self._v_state,
-                            acc=self._acc, stats=self._stats)
+            rows_q = self._rows_selected(index, count) // b
+            cols_k = self._rows_selected(index_k, count_k) // b
+            self._count_matmul_1(qkv, n_keys, rows_q, cols_k)
+            self.v_gate.counts["gate_flops"] += b * h * n_keys * dh
+            self.matmul_gate.counts["gate_flops"] += b * h * n * n_keys
+            self.matmul_accumulator_2.counts["accumulator_flops"] += b * (h * cols_k * dh + 2 * h * n * dh)
+            self.matmul_accumulator_2.matmul.counts["matmul_flops"] += 2 * b * h * n * cols_k * dh
+        return self._global(qkv, native.ATTN_DELTA, idx=index_k, count=count_k, a_state=self._a_state,
+                            v_state=self._v_state, acc=self._acc, stats=self._stats, kv_pooled=kvp)

@@ -109,9 +109,10 @@ class CountedLinear(_Counted):
             self._tally("bias_flops", n_rows * self.out_features)
         self._tally("linear_flops", n_rows * self.in_features * self.out_features)
 
-    def forward(self, x, act=native.ACT_NONE, out=None, idx=None):
-        y = native.linear(x.contiguous(), self.weight.detach(), self.bias.detach(), act=act, out=out, idx=idx)
-        self.count_linear(x.numel() // self.in_features)
+    def forward(self, x, act=native.ACT_NONE, out=None, idx=None, count=None, rows=None):
+        """`count`: device-side number of valid rows per batch entry; `rows`: their host-side total for the counters."""
+        y = native.linear(x.contiguous(), self.weight.detach(), self.bias.detach(), act=act, out=out, idx=idx, count=count)
+        self.count_linear(x.numel() // self.in_features if rows is None else rows)
         return y
 
     def forward_linear(self, x):

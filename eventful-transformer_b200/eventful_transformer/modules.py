@@ -47,8 +47,19 @@ class _FrameState(ExtendedModule):
 
     def _drop_state(self):
         self.first = True
+        self._last_sel = None
         for name in self._state:
             setattr(self, name, None)
+
+    # Selection trace of the fused block path (tests / visualisation): the index tensor the gate last used.  With a
+    # device-side count (threshold policy) the padded index is cut to its valid length here, on demand -- the only
+    # place that reads the count back to the host.
+    @property
+    def last_index(self):
+        if self._last_sel is None:
+            return None
+        index, count = self._last_sel
+        return index if count is None else index[..., : int(count.max().item())]
 
     def reset_self(self):
         self._drop_state()
@@ -169,11 +180,24 @@ class TokenBuffer(_FrameState):
 
 
 class _ProductState(_FrameState):
-    _state = ("product",)
+    _state = ("_product",)
 
     def __init__(self):
         super().__init__()
         self.matmul = CountedMatmul()
+        self._producer = None
+
+    # `product` is the stored state tensor; the fused Eventful blocks do not store the query-key product and install
+    # a producer that recomputes it from their QKV buffer on demand instead.
+    @property
+    def product(self):
+        if self._product is None and self._producer is not None and not self.first:
+            return self._producer()
+        return self._product
+
+    @product.setter
+    def product(self, value):
+        self._product = value
 
     def _first_product(self, a, b):
         self.first, self.product = False, self.matmul(a, b)

@@ -86,8 +86,6 @@ class RelativePositionEmbedding(ExtendedModule):
 
     def __init__(self, attention_size, embedding_size, head_dim, pool_size=None):
         super().__init__()
-        if pool_size is not None:
-            raise NotImplementedError("eventful_b200: K/V pooling (pool_size) is not implemented yet")
         self.attention_size = tuple(attention_size)
         self.embedding_size = tuple(embedding_size)
         self.pool_size = pool_size
@@ -99,7 +97,8 @@ class RelativePositionEmbedding(ExtendedModule):
         self.x_relative = None
 
     def tables(self):
-        """(y_relative (ah, ah, dh), x_relative (aw, aw, dh)), contiguous, cached until reset()."""
+        """(y_relative (ah, kh, dh), x_relative (aw, kw, dh)), contiguous, cached until reset(); the key axes are
+        (ah, aw) or, with K/V pooling, the pooled grid (ah / pool_h, aw / pool_w) (utils.py:185-188)."""
         if self.y_relative is None:
             self.y_relative = self._get_relative(self.y_embedding.detach(), 0).contiguous()
             self.x_relative = self._get_relative(self.x_embedding.detach(), 1).contiguous()
@@ -110,6 +109,8 @@ class RelativePositionEmbedding(ExtendedModule):
         if self.count_mode:
             dh = self.y_embedding.shape[1]
             a = self.attention_size
+            if self.pool_size is not None:  # pooled key axes (utils.py:143-147)
+                a = (a[0] // self.pool_size[0], a[1] // self.pool_size[1])
             self.einsum.counts["einsum_flops"] += batch_heads * n_query * dh * (a[0] + a[1])
             self.add.counts["add_flops"] += 2 * batch_heads * n_query * n_key
 
@@ -117,6 +118,8 @@ class RelativePositionEmbedding(ExtendedModule):
         """Stand-alone form on materialised logits x (B, H, N, N); library ops, off the fused path."""
         a = self.attention_size
         y_rel, x_rel = self.tables()
+        if self.pool_size is not None:
+            raise NotImplementedError("the stand-alone rel-pos form is un-pooled; pooled keys run in the fused kernels")
         xs = x.view(x.shape[:2] + a + a)
         qs = q.reshape(q.shape[:2] + a + q.shape[-1:])
         term = self.einsum("abhwc,hkc->abhwk", qs, y_rel).unsqueeze(-1)
@@ -134,6 +137,8 @@ class RelativePositionEmbedding(ExtendedModule):
             rel = rel.transpose(0, 2).unsqueeze(0)
             rel = func.interpolate(rel, self.attention_size, mode="bicubic", align_corners=False)
             rel = rel.squeeze(0).transpose(0, 2)
+        if self.pool_size is not None:  # average the key axis over the pooling cells (one-off table preparation)
+            rel = func.avg_pool1d(rel.transpose(1, 2), self.pool_size[dim]).transpose(1, 2)
         return rel
 
     def reset_self(self):

@@ -115,7 +115,8 @@ float et_debug_elapsed_ms(void);
  *   blocks.py:242-246 (mlp_1 + GELU + mlp_2), fused with TokenBuffer.scatter_ (modules.py:96).
  *   A (M, K), W (n_feat, K) torch Linear layout (counting.py:142-143), bias (n_feat).
  *   count (M / k) int32 or NULL: device-side valid rows per batch entry.
- * dtype must be ET_BF16 or ET_F16 (fp32 accumulate).
+ * ET_BF16 / ET_F16: tcgen05 tensor cores, fp32 accumulate.  ET_F32: fp32 SGEMM on the CUDA cores (fp32 models,
+ * BASELINE configs[0] and the reference's timed CUDA config, configs/time/vitdet_vid/_cuda.yml).
  */
 int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bias, int64_t n_feat, int act,
               void* out, int64_t ld_out, const int64_t* idx, const int32_t* count, int64_t k,
@@ -130,14 +131,15 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
  *   qkv (B, gh*gw + extra, 3*H*dh); pad_token (3*H*dh) = qkv.bias (blocks.py:275-287);
  *   rel_y (wh, wh, dh), rel_x (ww, ww, dh) relative tables or NULL; out (B, N, H*dh).
  *   window (wh, ww) = (0, 0) means one global window over all tokens (incl. class token).
+ *   ET_F32 runs in fp32 arithmetic on the CUDA cores and always needs the workspace (softmax statistics).
  */
 int et_window_attention(const void* qkv, const void* pad_token, const void* rel_y, const void* rel_x, void* out,
                         void* workspace, int64_t B, int64_t N, int64_t gh, int64_t gw, int64_t wh, int64_t ww,
                         int64_t heads, int64_t dh, int dtype, void* stream);
 
-/* Bytes of caller-provided scratch (`workspace`) the two attention entry points need:
- * rel-pos bias tables (B, H, N, gh + gw) and, for the global DELTA mode, the v-gate deltas 2 x (B, k, H*dh).
- * Pass wh = ww = 0 for global attention. */
+/* Bytes of caller-provided scratch (`workspace`) the two attention entry points need (upper bound over all code
+ * paths): rel-pos bias tables (B, H, N, gh + gw), for the global DELTA mode the v-gate deltas 2 x (B, k, H*dh), and
+ * the fp32 softmax statistics of the general-precision path.  Pass wh = ww = 0 for global attention. */
 int64_t et_attn_workspace_bytes(int64_t B, int64_t N, int64_t gh, int64_t gw, int64_t wh, int64_t ww,
                                 int64_t heads, int64_t dh, int64_t k, int has_relpos);
 
@@ -152,23 +154,52 @@ int64_t et_attn_workspace_bytes(int64_t B, int64_t N, int64_t gh, int64_t gw, in
  * Replaces: MatmulBuffer (modules.py:204-252; the product is recomputed, it always equals
  *   (q/scale) k^T of the current buffer), softmax (blocks.py:522), TokenDeltaGate x2
  *   (blocks.py:567-568, modules.py:187-201), MatmulDeltaAccumulator (modules.py:285-295),
- *   RelativePositionEmbedding.forward(inplace=False) (blocks.py:521).
- *   qkv (B, N, 3*H*dh); rel_y (gh, gh, dh) / rel_x (gw, gw, dh) or NULL (class-token models);
- *   a_state (B, H, N, NP) stored COLUMN-major per head: a_state[b][h][col][row], row stride
+ *   RelativePositionEmbedding.forward(inplace=False) (blocks.py:521), Block._cast_matmul_2 /
+ *   _uncast_matmul_2 (blocks.py:183-189,393-396) and the pooled-key variants (blocks.py:509-511).
+ *   qkv (B, N, 3*H*dh);
+ *   kv_pooled NULL, or (B, Nk, 2*H*dh) = [k | v] averaged over pool_h x pool_w cells of the token grid
+ *           (et_pool_kv; Nk = (gh / pool_h) * (gw / pool_w)); idx then holds pooled-cell ids (et_pool_index);
+ *   rel_y (gh, kh, dh) / rel_x (gw, kw, dh) or NULL (class-token models); kh = gh / pool_h, kw = gw / pool_w
+ *           (tables averaged along the key axis, utils.py:185-188; kh = gh, kw = gw without pooling);
+ *   count NULL, or (B) int32 on the device: number of valid entries of idx per batch entry (threshold policy,
+ *           pooled unique indices); k is then the row stride of idx and the upper bound;
+ *   state_dtype: element type of a_state / v_state / acc (matmul_2_cast); out has the model dtype;
+ *   a_state (B, H, Nk, NP) stored COLUMN-major per head: a_state[b][h][col][row], row stride
  *           NP = N rounded up to a multiple of 8 (16-byte segments of a selected column);
- *   v_state (B, N, H*dh); acc (B, N, H*dh); out (B, N, H*dh); idx (B, k).
+ *   v_state (B, Nk, H*dh); acc (B, N, H*dh); out (B, N, H*dh); idx (B, k).
  *   row_stats (B, H, N, 2) float workspace (row max, row sum).
+ * 16-bit models whose state has the model dtype and un-pooled keys run on the tcgen05 / mma.sync tensor-core
+ * kernels; fp32 models, state_dtype != dtype and pooled keys run in fp32 arithmetic on the CUDA cores.
  */
-int et_global_attention(const void* qkv, const void* rel_y, const void* rel_x, int mode, const int64_t* idx,
-                        int64_t k, void* a_state, void* v_state, void* acc, void* out, float* row_stats,
-                        void* workspace, int64_t B, int64_t N, int64_t gh, int64_t gw, int64_t heads, int64_t dh,
-                        int dtype, void* stream);
+int et_global_attention(const void* qkv, const void* kv_pooled, int64_t pool_h, int64_t pool_w, const void* rel_y,
+                        const void* rel_x, int mode, const int64_t* idx, const int32_t* count, int64_t k, void* a_state,
+                        void* v_state, void* acc, void* out, float* row_stats, void* workspace, int64_t B, int64_t N,
+                        int64_t gh, int64_t gw, int64_t heads, int64_t dh, int dtype, int state_dtype, void* stream);
 
-/* Generic strided batched matmul C = A @ B (fp32 accumulate) for the stand-alone
- * MatmulBuffer / MatmulDeltaAccumulator modules (counting.py:165-175). Element strides. */
-int et_bmm(const void* A, const void* Bm, void* C, int64_t batch, int64_t M, int64_t N, int64_t K,
-           int64_t sab, int64_t sam, int64_t sak, int64_t sbb, int64_t sbk, int64_t sbn, int64_t scb,
-           int64_t scm, int64_t scn, int accumulate, int dtype, void* stream);
+/*
+ * K/V token pooling (Block._pool_tokens, blocks.py:303-326): out (B, Nk, 2*D) = avg_pool2d of the k and v parts of
+ * qkv (B, gh*gw, 3*D) over pool_h x pool_w cells (fp32 average, rounded to dtype).
+ */
+int et_pool_kv(const void* qkv, void* out, int64_t B, int64_t gh, int64_t gw, int64_t D, int64_t pool_h, int64_t pool_w,
+               int dtype, void* stream);
+
+/*
+ * EventfulMatmul1Block._pool_index (blocks.py:525-540): token indices idx (B, k) [first count_in[b] valid, or all
+ * k when count_in is NULL] -> pooled-cell ids, ascending and unique per batch entry: out_idx (B, k), out_count (B).
+ * (For B > 1 the reference's unique(dim=-1) de-duplicates columns jointly and can leave duplicates inside a row,
+ * which double-counts deltas downstream; this entry point de-duplicates per row.)
+ */
+int et_pool_index(const int64_t* idx, const int32_t* count_in, int64_t B, int64_t k, int64_t gh, int64_t gw, int64_t pool_h,
+                  int64_t pool_w, int64_t* out_idx, int32_t* out_count, void* stream);
+
+/* Generic strided batched matmul C = alpha * (A @ B) [+ C] (fp32 accumulate, result rounded to dtype before the
+ * optional in-place add) for the stand-alone MatmulBuffer / MatmulDeltaAccumulator / CountedMatmul modules
+ * (modules.py:204-299, counting.py:165-175).  Two batch levels (batch_outer x batch_inner, e.g. batch x heads) so
+ * that permuted views of a QKV buffer need no copy; strides_* are HOST arrays of 4 element strides each:
+ * {outer batch, inner batch, row, column} of A (M x K), B (K x N) and C (M x N). */
+int et_bmm(const void* A, const void* Bm, void* C, int64_t batch_outer, int64_t batch_inner, int64_t M, int64_t N,
+           int64_t K, const int64_t* strides_a, const int64_t* strides_b, const int64_t* strides_c, int accumulate,
+           float alpha, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

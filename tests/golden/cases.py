@@ -68,6 +68,14 @@ CASES = {
     "vitdet_b_672": dict(cfg=VITDET_B_FULL, input_size=(42, 42), batch=1, frames=3, policy=("topk", dict(k=512)),
                          block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
                          std=0.02, stream="drift", seed=13, subsample=True),
+    # the reference's timed CUDA configuration (configs/time/vitdet_vid/_cuda.yml): fp32 model, fp16 attention-value path
+    "small_cast16": dict(cfg=SMALL_B, input_size=(16, 16), batch=1, frames=4, policy=("topk", dict(k=64)),
+                         block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock", matmul_2_cast="float16",
+                         std=0.04, stream="drift", seed=18, subsample=True),
+    # the "spatial" configuration (configs/evaluate/vitdet_vid/_spatial.yml): 2 x 2 K/V pooling on the global block only
+    "small_pool": dict(cfg=SMALL_B, input_size=(16, 16), batch=1, frames=4, policy=("topk", dict(k=64)),
+                       block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock", pool_size=(2, 2),
+                       std=0.04, stream="drift", seed=19, subsample=True),
     # the BENCHMARKED configuration (BASELINE configs[1]): 1024 x 1024 -> 64 x 64 tokens, 25 padded 14 x 14 windows,
     # k = 2048 of 4096; 4 frames so that the CUDA-graph path (captured at frame 2) is replayed at least once
     "vitdet_b_1024": dict(cfg=VITDET_B_FULL, input_size=(64, 64), batch=1, frames=4, policy=("topk", dict(k=2048)),

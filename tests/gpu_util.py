@@ -9,10 +9,12 @@ import et_synthetic as syn
 DEV = "cuda"
 
 
-def build_gpu_backbone(case, params, dtype=torch.bfloat16):
+def build_gpu_backbone(case, params, dtype=torch.bfloat16, cast=None):
+    """`cast`: matmul_2_cast of the global blocks (the windowed ones get null, as in the reference's configs)."""
     kw = syn.backbone_kwargs(case["cfg"], case["input_size"], block_class=case["block_class"],
                              windowed_class=case.get("windowed_class", "EventfulTokenwiseBlock"),
-                             matmul_2_cast=None, has_class_token=case.get("has_class_token", False))
+                             matmul_2_cast=cast, has_class_token=case.get("has_class_token", False),
+                             pool_size=case.get("pool_size"))
     if kw.get("windowed_class") is None:
         kw.pop("windowed_class", None)
     for flag in ("gate_before_ln", "stgt"):

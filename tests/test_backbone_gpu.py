@@ -12,7 +12,7 @@ DT = torch.bfloat16
 
 
 def run_gpu(case, params, frames, graph=False):
-    model = build_gpu_backbone(case, params, DT)
+    model = build_gpu_backbone(case, params, DT, cast=case.get("matmul_2_cast"))
     model.use_cuda_graph = graph
     outs, traces = [], []
     with torch.inference_mode():
@@ -37,8 +37,8 @@ def _compare_selections(name, t, oracle, forced, case, tag):
     return stats
 
 
-# K/V pooling has its own tests (test_variants_gpu.py)
-@pytest.mark.parametrize("name", sorted(n for n, c in CASES.items() if not c.get("pool_size")))
+# K/V pooling and the fp16 attention-value path have their own tests (test_variants_gpu.py)
+@pytest.mark.parametrize("name", sorted(n for n, c in CASES.items() if not c.get("pool_size") and c.get("matmul_2_cast") != "float16"))
 def test_backbone_matches_oracle_given_identical_index_sets(name):
     """
     Activations: given identical index sets, the bf16 CUDA output must be as close to the exact
@@ -90,8 +90,12 @@ def test_backbone_matches_oracle_given_identical_index_sets(name):
                 if first is not None and lowp is not None:
                     first_gate_edge = max(first_gate_edge, first[1])
                     assert first[0] >= 0.98 and first[1] <= 2.0 ** -5, f"{name} frame {t}: first gate {first}"
+                # measured on B200 (profiles/r2_parity_measured.md): overlap >= 0.89 at k >= 64, boundary distance <= 0.074
                 for key, (overlap, edge) in stats.items():
-                    assert overlap >= 0.80 and edge <= 0.35, f"{name} frame {t} gate {key}: overlap {overlap:.3f}, boundary distance {edge:.3f}"
+                    k_sel = forced[key].shape[-1]
+                    differing = round((1.0 - overlap) * k_sel)
+                    assert differing <= max(1, 0.12 * k_sel) and edge <= 0.15, \
+                        f"{name} frame {t} gate {key}: {differing} of {k_sel} tokens differ, boundary distance {edge:.3f}"
     if policy_driven:
         record("selection_vs_oracle", case=name, worst_overlap=worst_overlap, worst_boundary_distance=worst_edge,
                first_gate_boundary_distance=first_gate_edge)

@@ -19,7 +19,7 @@ def _rand(shape, g, dtype):
 def test_matmul_buffer_rows_then_columns(dtype):
     """modules.py:204-252: rows index_q, then columns index_k of the stored product are refreshed; returns the state."""
     g = torch.Generator().manual_seed(41)
-    b, h, n, dh, k = 2, 3, 50, 32, 11
+    b, h, n, dh, k = 2, 3, 64, 32, 12  # rows of the (n x n) product are 16-byte multiples in every dtype
     buf, st = modules.MatmulBuffer(), {}
     buf.counting()
     q = _rand((b, h, n, dh), g, dtype)

@@ -1,0 +1,187 @@
+"""
+GPU parity of the variants of SURVEY 8(f3) and of the fp32 path:
+  * fp32 models (BASELINE configs[0]): the CUDA path runs FREE (its own selections) and must reproduce the
+    reference fixtures -- same selected index sets, outputs to fp32 rounding;
+  * matmul_2_cast != model dtype (the reference's timed CUDA config: fp32 model, fp16 attention-value path);
+  * K/V pooling with _pool_index (data-dependent number of selected keys, device-side count);
+  * TokenNormThreshold without any host synchronisation (device-side count, CUDA-graph capturable).
+"""
+import numpy as np
+import pytest
+import torch
+
+from cases import CASES
+from golden_util import case_frames, case_params, load_golden, oracle_for, subsample
+from gpu_util import DEV, allclose_report, build_gpu_backbone, elem_err, gpu_trace, record, rel_err, rounded
+
+pytestmark = pytest.mark.gpu
+
+
+def run_free(case, params, frames, dtype, cast=None, graph=False):
+    model = build_gpu_backbone(case, params, dtype, cast=cast)
+    model.use_cuda_graph = graph
+    outs, traces = [], []
+    with torch.inference_mode():
+        for x in frames:
+            outs.append(model(x.to(dtype).to(DEV)).float().cpu())
+            traces.append(gpu_trace(model))
+    return model, outs, traces
+
+
+FP32_CASES = sorted(n for n, c in CASES.items() if not c.get("matmul_2_cast"))
+
+
+@pytest.mark.parametrize("name", FP32_CASES)
+def test_fp32_free_running_reproduces_the_reference_fixture(name):
+    """
+    fp32 end to end on the GPU, nothing forced: every frame's output and EVERY gate's selected index set are compared
+    with what the unmodified reference produced on the same seeded inputs (tests/golden/*.npz).
+    Index sets must be identical (a token may differ only if its norm ties with the k-th norm to fp32 rounding:
+    at most 0.2 % of a set); outputs within 2e-4 of the output range (5e-3 once a tie has flipped).
+    """
+    case, gold = CASES[name], load_golden(name)
+    params, frames = case_params(case), case_frames(case)
+    _, outs, traces = run_free(case, params, frames, torch.float32)
+    exact_sets, total_sets, worst_overlap, flipped = 0, 0, 1.0, False
+    for t in range(case["frames"]):
+        for (i, gate), idx in traces[t].items():
+            want = gold[f"idx_{t}_{i}_{gate}"]
+            got = np.sort(idx.numpy(), axis=-1)
+            total_sets += 1
+            if got.shape == want.shape and np.array_equal(got, want):
+                exact_sets += 1
+                continue
+            flipped = True
+            for r in range(want.reshape(-1, want.shape[-1]).shape[0]):
+                a = set(got.reshape(-1, got.shape[-1])[r].tolist())
+                b = set(want.reshape(-1, want.shape[-1])[r].tolist())
+                overlap = len(a & b) / max(1, max(len(a), len(b)))
+                worst_overlap = min(worst_overlap, overlap)
+        n_gold = sum(1 for f in gold.files if f.startswith(f"idx_{t}_"))
+        assert len(traces[t]) == n_gold, f"{name} frame {t}: {len(traces[t])} gates traced, fixture has {n_gold}"
+        want = torch.from_numpy(gold[f"out_{t}"])
+        got = subsample(outs[t]) if case.get("subsample") else outs[t]
+        err = rel_err(got, want)
+        record("fp32_vs_reference_fixture", case=name, frame=t, rel_err_of_range=err, exact_sets=exact_sets,
+               total_sets=total_sets, worst_overlap=worst_overlap)
+        assert err <= (5e-3 if flipped else 2e-4), f"{name} frame {t}: rel err {err:.2e} (flipped={flipped})"
+    assert worst_overlap >= 0.998, f"{name}: worst index-set overlap {worst_overlap:.4f}"
+    record("fp32_index_sets", case=name, exact_sets=exact_sets, total_sets=total_sets, worst_overlap=worst_overlap)
+
+
+@pytest.mark.parametrize("name,model_dtype", [("tiny_cast", torch.float32), ("small_cast16", torch.float32),
+                                              ("small_cast16", torch.bfloat16)])
+def test_matmul_2_cast_differs_from_model_dtype(name, model_dtype):
+    """
+    a, v, the v-gate / A-gate state and the accumulator live in the cast dtype, q k^T and the softmax in the model dtype
+    (blocks.py:183-189,561-562,574).  fp32 model: free-running against the reference fixture (16-bit noise in a and v only:
+    selections may differ at near-ties); state dtypes are checked explicitly.
+    """
+    case, gold = CASES[name], load_golden(name)
+    cast = case["matmul_2_cast"]
+    params = case_params(case)
+    frames = [f.to(model_dtype).float() for f in case_frames(case)]
+    model, outs, traces = run_free(case, params, frames, model_dtype, cast=cast)
+    glob = [b for b in model.blocks if hasattr(b, "matmul_gate")]
+    assert glob and all(b.matmul_gate.p.dtype == getattr(torch, cast) for b in glob)
+    assert all(b.v_gate.p.dtype == getattr(torch, cast) and b.matmul_accumulator_2.product.dtype == getattr(torch, cast)
+               for b in glob)
+    assert outs[0].dtype == torch.float32
+    oracle = oracle_for(case, params if model_dtype == torch.float32 else rounded(params, model_dtype))
+    with torch.inference_mode():
+        for t, x in enumerate(frames):
+            want = oracle.forward(x.clone(), forced=traces[t])
+            err = rel_err(outs[t], want)
+            record("matmul_2_cast", case=name, model=str(model_dtype), frame=t, rel_err_of_range=err)
+            assert err <= (5e-3 if model_dtype == torch.float32 else 4e-2), f"{name} frame {t}: {err:.4f}"
+    if model_dtype == torch.float32:  # and straight against the reference's own outputs (free-running both sides)
+        for t in range(case["frames"]):
+            want = torch.from_numpy(gold[f"out_{t}"])
+            got = subsample(outs[t]) if case.get("subsample") else outs[t]
+            err = rel_err(got, want)
+            record("matmul_2_cast_vs_fixture", case=name, frame=t, rel_err_of_range=err)
+            assert err <= 2e-2, f"{name} frame {t}: {err:.4f}"
+
+
+POOL_CASES = sorted(n for n, c in CASES.items() if c.get("pool_size"))
+
+
+@pytest.mark.parametrize("name", POOL_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_kv_pooling_and_pool_index(name, dtype):
+    """
+    K/V pooling (blocks.py:303-326) + _pool_index (blocks.py:525-540): pooled keys / values, pooled rel-pos tables, a
+    sorted unique pooled index of data-dependent length driving the v-gate, the A-gate and the accumulator through a
+    device-side count.  fp32: free-running against the reference fixture; bf16: against the oracle replaying the CUDA selections.
+    """
+    case, gold = CASES[name], load_golden(name)
+    params = case_params(case)
+    frames = [f.to(dtype).float() for f in case_frames(case)]
+    model, outs, traces = run_free(case, params, frames, dtype)
+    if dtype == torch.float32:
+        for t in range(case["frames"]):
+            want = torch.from_numpy(gold[f"out_{t}"])
+            got = subsample(outs[t]) if case.get("subsample") else outs[t]
+            err = rel_err(got, want)
+            record("kv_pooling_fp32_vs_fixture", case=name, frame=t, rel_err_of_range=err)
+            assert err <= 2e-4, f"{name} frame {t}: {err:.2e}"
+            for (i, gate), idx in traces[t].items():
+                assert np.array_equal(np.sort(idx.numpy(), axis=-1), gold[f"idx_{t}_{i}_{gate}"]), (t, i, gate)
+    else:
+        oracle = oracle_for(case, rounded(params, dtype))
+        with torch.inference_mode():
+            for t, x in enumerate(frames):
+                want = oracle.forward(x.clone(), forced=traces[t] if case["policy"] is not None else None)
+                err = rel_err(outs[t], want)
+                record("kv_pooling_bf16_vs_oracle", case=name, frame=t, rel_err_of_range=err)
+                assert err <= 4e-2, f"{name} frame {t}: {err:.4f}"
+
+
+def test_pool_index_kernel_matches_unique():
+    """et_pool_index against the reference expression (blocks.py:529-539) on random and degenerate index sets."""
+    from eventful_transformer import _native as native
+
+    g = torch.Generator().manual_seed(61)
+    for gh, gw, pool, k in [(64, 64, (2, 2), 2048), (6, 6, (2, 2), 10), (12, 8, (3, 2), 96), (42, 42, (2, 2), 1), (8, 8, (2, 2), 64)]:
+        idx = torch.stack([torch.randperm(gh * gw, generator=g)[:k] for _ in range(3)])
+        out, count = native.pool_index(idx.to(DEV), None, (gh, gw), pool)
+        for r in range(3):
+            iy = idx[r].div(gw, rounding_mode="floor").div(pool[0], rounding_mode="floor")
+            ix = idx[r].remainder(gw).div(pool[1], rounding_mode="floor")
+            want = (iy * (gw // pool[1]) + ix).unique()
+            n = int(count[r])
+            assert n == want.numel() and torch.equal(out[r, :n].cpu(), want), (gh, gw, pool, k, r)
+    # with a device-side input count only the first count[b] entries take part
+    idx = torch.arange(36).view(1, 36)
+    cnt = torch.tensor([5], dtype=torch.int32)
+    out, count = native.pool_index(idx.to(DEV), cnt.to(DEV), (6, 6), (2, 2))
+    assert int(count[0]) == 3 and out[0, :3].tolist() == [0, 1, 2]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_threshold_policy_runs_without_host_sync_and_in_a_cuda_graph(dtype):
+    """
+    TokenNormThreshold inside the blocks: the number of selected tokens stays on the device (padded index + count), so
+    the frame is a fixed launch sequence -- captured in a CUDA graph here -- and must equal the eager run bit for bit.
+    The selections are data-dependent in size; they are compared with the oracle replaying them.
+    """
+    case = dict(CASES["tiny_threshold"], frames=6)
+    params = case_params(case)
+    frames = [f.to(dtype).float() for f in case_frames(case)]
+    _, eager, traces = run_free(case, params, frames, dtype, graph=False)
+    model, graphed, traces_g = run_free(case, params, frames, dtype, graph=True)
+    assert model._graph is not None, "threshold frames were not captured"
+    sizes = set()
+    for t in range(case["frames"]):
+        assert torch.equal(eager[t], graphed[t]), t
+        for key, idx in traces[t].items():
+            assert torch.equal(idx, traces_g[t][key]), (t, key)
+            sizes.add(idx.shape[-1])
+    assert len(sizes) > 2, f"threshold selections should vary in size, got {sorted(sizes)}"
+    oracle = oracle_for(case, rounded(params, dtype) if dtype != torch.float32 else params)
+    with torch.inference_mode():
+        for t, x in enumerate(frames):
+            want = oracle.forward(x.clone(), forced=traces[t])
+            err = rel_err(eager[t], want)
+            record("threshold_device_count", dtype=str(dtype), frame=t, rel_err_of_range=err)
+            assert err <= (2e-4 if dtype == torch.float32 else 4e-2), (t, err)
