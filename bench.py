@@ -49,7 +49,9 @@ def parse_args():
     ap.add_argument("--k", type=int, default=2048)
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--quick", action="store_true", help="skip dense comparators, kernel leg and CPU baseline")
+    ap.add_argument("--quick", action="store_true", help="skip dense comparators, kernel leg, other configs and CPU baseline")
+    ap.add_argument("--total-streams", type=int, default=64,
+                    help="BASELINE configs[4]: total concurrent streams partitioned over the GPUs (strong-scaling leg)")
     return ap.parse_args()
 
 
@@ -172,6 +174,129 @@ def run_stream_model(model, frames_dev, warmup, steps, dist_ctx, use_graph):
 
         ms = timed_steps(step, steps, dist_ctx)
     return ms, per_step, base + steps
+
+
+# ------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations (reported inside the same JSON line as `configs`)
+# ------------------------------------------------------------------------------------------
+VIVIT_B_SPATIAL = dict(depth=12, dim=768, heads=12, mlp_ratio=4, position_encoding_size=(14, 14))  # configs/models/vivit_b_kinetics400.yml
+VIVIT_B_EPIC = dict(depth=12, dim=768, heads=12, mlp_ratio=4, position_encoding_size=(20, 20))     # configs/models/vivit_b_epic_kitchens.yml
+
+
+def build_model(cfg, grid, device, dtype, policy=None, block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
+                has_class_token=False, cast=None, pool=None):
+    from eventful_transformer import backbones, modules
+
+    kw = syn.backbone_kwargs(cfg, grid, block_class=block_class, windowed_class=windowed_class, matmul_2_cast=cast,
+                             has_class_token=has_class_token, pool_size=pool)
+    model = backbones.ViTBackbone(**kw)
+    model.load_state_dict(syn.seeded_params(cfg, seed=0, std=0.02, has_class_token=has_class_token), strict=True)
+    model = model.to(device).to(dtype).eval()
+    if policy is not None:
+        for cls in (modules.SimpleSTGTGate, modules.TokenDeltaGate, modules.TokenGate):
+            for gate in model.modules_of_type(cls):
+                gate.policy = policy()
+    return model
+
+
+def side_config(label, cfg, grid, batch, device, dtype, policy, steps, warmup=3, has_class_token=False, cast=None, pool=None,
+                stream_mode="drift"):
+    """One of the other BASELINE configurations: device-resident inputs, CUDA-graph replay, incremental frames only."""
+    n = grid[0] * grid[1] + int(has_class_token)
+    model = build_model(cfg, grid, device, dtype, policy=policy, has_class_token=has_class_token, cast=cast, pool=pool)
+    frames = [f.to(device) for f in syn.token_stream(batch, n, cfg["dim"], RING, seed=7, mode=stream_mode, dtype=dtype)]
+    ms, per_step, _ = run_stream_model(model, frames, warmup, steps, None, True)
+    out = dict(workload=label, value=round(steps * batch / (ms * 1e-3), 2), unit=UNIT, ms_per_step=round(ms / steps, 4),
+               batch=batch, tokens=n, dtype=str(dtype).replace("torch.", ""), launches_per_step=int(per_step), steps=steps,
+               cuda_graph=model._graph is not None)
+    selected = {}
+    for i, blk in enumerate(model.blocks):
+        gate = getattr(blk, "qkv_gate", None)
+        if gate is not None and gate.last_index is not None:
+            selected[i] = int(gate.last_index.shape[-1])
+    if selected:
+        out["selected_tokens_last_frame"] = dict(min=min(selected.values()), max=max(selected.values()))
+    del model, frames
+    torch.cuda.empty_cache()
+    return out
+
+
+def other_configs(device, steps):
+    """BASELINE.json configs[0], [2], [3] on this GPU (configs[1] is the headline, configs[4] the stream legs)."""
+    from eventful_transformer import policies
+
+    out = {}
+    topk = lambda k: (lambda: policies.TokenNormTopK(k=k))  # noqa: E731
+    with torch.inference_mode():
+        # configs[0]: ViTDet-B 672^2, 1 stream, k = 512 of 1764 -- in fp32 (the dtype the reference's CPU run uses), in the
+        # reference's own timed CUDA setting (fp32 model, fp16 attention-value path) and in bf16
+        for tag, dt, cast in (("c0_vitdet_b_672_fp32", torch.float32, None), ("c0_vitdet_b_672_fp32_fp16av", torch.float32, "float16"),
+                              ("c0_vitdet_b_672_bf16", torch.bfloat16, None)):
+            out[tag] = side_config("ViTDet-B 672x672, 1 stream, TopK k=512 of 1764" + (f", matmul_2_cast={cast}" if cast else ""),
+                                   syn.VITDET_B, (42, 42), 1, device, dt, topk(512), steps, cast=cast)
+        # configs[2]: ViViT-B spatial sub-model, Kinetics-400 shape: 12 views batched, 196 + class token, k = 64
+        out["c2_vivit_b_k400_spatial"] = side_config(
+            "ViViT-B spatial encoder (K400 shape): 12 views x 197 tokens per step, TopK k=64", VIVIT_B_SPATIAL, (14, 14), 12, device,
+            torch.bfloat16, topk(64), steps, has_class_token=True)
+        # configs[3]: ViViT-B EPIC-Kitchens shape: 320^2 -> 400 + class token, threshold policy (batch 1, device-side counts)
+        for thr in (0.2, 1.0, 5.0):
+            out[f"c3_vivit_b_epic_threshold_{thr}"] = side_config(
+                f"ViViT-B spatial encoder (EPIC-Kitchens shape): 1 view x 401 tokens per step, TokenNormThreshold {thr}",
+                VIVIT_B_EPIC, (20, 20), 1, device, torch.bfloat16, (lambda thr=thr: policies.TokenNormThreshold(threshold=thr)),
+                steps, has_class_token=True)
+    return out
+
+
+def k_sweep(grid, streams, frames_dev, device, dtype, steps, dense_fps):
+    """configs[4]: frames/s at k = 512 ... 4096 for one stream group on this GPU, next to the dense (ungated) model."""
+    out = {}
+    for k in (512, 1024, 2048, 3072, 4096):
+        model = make_backbone(grid, "EventfulBlock", "EventfulTokenwiseBlock", k, device, dtype)
+        ms, _, _ = run_stream_model(model, frames_dev, 3, steps, None, True)
+        fps = steps * streams / (ms * 1e-3)
+        out[str(k)] = dict(value=round(fps, 2), ms_per_step=round(ms / steps, 4),
+                           speedup_vs_fused_dense=None if dense_fps is None else round(fps / dense_fps, 3))
+        del model
+        torch.cuda.empty_cache()
+    return out
+
+
+def partitioned_streams_leg(grid, total_streams, world, rank, device, dtype, k, steps, dist_ctx, bytes_per_stream):
+    """
+    configs[4]: a FIXED total of concurrent streams partitioned over the ranks (strong scaling: 64 -> 64/32/16/8 per GPU).
+    Skipped (with the reason) when a rank's share does not fit its memory.
+    """
+    mine = et_streams.partition_streams(total_streams, world, rank)
+    free, total = torch.cuda.mem_get_info(device)
+    need = len(mine) * bytes_per_stream * 1.08 + (8 << 30)
+    fits = torch.tensor([1.0 if need < free else 0.0], device=device)
+    if dist_ctx is not None:
+        dist_ctx.all_reduce(fits, op=dist_ctx.ReduceOp.MIN)
+    if float(fits.item()) < 1.0:
+        return dict(total_streams=total_streams, streams_per_gpu=len(mine), unavailable=
+                    f"needs ~{need / 2**30:.0f} GiB per GPU for {len(mine)} resident streams, {free / 2**30:.0f} GiB free")
+    n, d = grid[0] * grid[1], syn.VITDET_B["dim"]
+    try:
+        model = make_backbone(grid, "EventfulBlock", "EventfulTokenwiseBlock", k, device, dtype)
+        ring = 4
+        per_stream = [syn.token_stream(1, n, d, ring, seed=et_streams.stream_seed(100, sid), mode="drift", dtype=dtype) for sid in mine]
+        frames = [torch.cat([f[t] for f in per_stream], dim=0).to(device) for t in range(ring)]
+        del per_stream
+        model.reset()
+        model.use_cuda_graph = True
+        with torch.inference_mode():
+            model(frames[0])
+            for t in range(1, 4):
+                model(frames[t % ring])
+            ms = timed_steps(lambda i: model(frames[(4 + i) % ring]), steps, dist_ctx)
+        out = dict(total_streams=total_streams, streams_per_gpu=len(mine), value=round(steps * total_streams / (ms * 1e-3), 2),
+                   unit=UNIT, ms_per_step=round(ms / steps, 4), steps=steps, scaling="strong",
+                   resident_state_gib_per_gpu=round(torch.cuda.max_memory_allocated(device) / 2**30, 1))
+    except torch.OutOfMemoryError as exc:  # never take the box down: report and move on
+        out = dict(total_streams=total_streams, streams_per_gpu=len(mine), unavailable=f"out of memory: {str(exc)[:120]}")
+    model = frames = None
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -336,7 +461,9 @@ def kernel_leg(streams, n, d, k, grid, pk):
 # ------------------------------------------------------------------------------------------
 # CPU baseline / reference arm (the oracle port of the reference algorithm on the host cores)
 # ------------------------------------------------------------------------------------------
-def cpu_reference(grid, k, steps, warmup, budget_s):
+def cpu_reference(grid, k, steps, warmup, budget_s, threads=None):
+    if threads is not None:
+        torch.set_num_threads(int(threads))
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import eventful_oracle as orc  # the one place bench.py executes oracle/
 
@@ -473,6 +600,15 @@ def main():
                          ms_per_step=round(ms_e2e / args.steps, 4)),
                 gpu_launches=int(per_step * args.steps), launches_per_step=int(per_step), clocks=clocks)
 
+    # ---- configs[4]: a fixed total of streams partitioned over the GPUs (every rank takes part; strong scaling)
+    bytes_per_stream = torch.cuda.max_memory_allocated(dev) / max(1, args.streams)
+    del pipe, model
+    torch.cuda.empty_cache()
+    if not args.quick and args.total_streams > 0:
+        torch.cuda.reset_peak_memory_stats(dev)
+        line["partitioned_streams"] = partitioned_streams_leg(grid, args.total_streams, world, rank, dev, dt, args.k,
+                                                              max(3, args.steps // 4), dist_ctx, bytes_per_stream)
+
     if rank == 0 and args.streams != 1:
         # the latency case: ONE stream on this GPU (same model, own state), device-resident inputs, CUDA-graph replay
         one = make_backbone(grid, "EventfulBlock", "EventfulTokenwiseBlock", args.k, dev, dt)
@@ -517,12 +653,22 @@ def main():
                                 share_of_step=round(kt["ms"] * kt["per_step"] / (ms / args.steps), 3))
         line["kernels"] = kernels
         if world == 1:
-            torch.set_num_threads(os.cpu_count() or 1)
-            r = cpu_reference(grid, args.k, 2, 0, budget_s=40.0)
+            # BASELINE configs[4] k-sweep and configs[0], [2], [3] on this GPU
+            with torch.inference_mode():
+                line["k_sweep"] = dict(streams_per_gpu=args.streams, fused_dense_fps=round(dense_fps, 2),
+                                       by_k=k_sweep(grid, args.streams, frames_dev, dev, dt, max(5, args.steps // 3), dense_fps))
+            line["configs"] = other_configs(dev, max(10, args.steps))
+            # the reference algorithm on the host cores: at the reference's own thread setting (configs/time/vitdet_vid/_cpu.yml:
+            # threads 8) and on all cores
+            cores = os.cpu_count() or 1
+            r8 = cpu_reference(grid, args.k, 2, 0, budget_s=25.0, threads=min(8, cores))
+            r = cpu_reference(grid, args.k, 2, 0, budget_s=25.0, threads=cores)
+            sample = ("1 stream: dense flush then {t} incremental frame(s) of the same ViTDet-B 1024^2 k={k} workload, fp32 with "
+                      "bf16 attention-value path (configs/time/vitdet_vid/_cpu.yml)")
             line["cpu_baseline"] = dict(value=round(r["fps"], 4), unit=UNIT, cores=r["cores"], kind="port",
-                                        sample=f"1 stream: dense flush then {r['timed']} incremental frame(s) of the "
-                                               f"same ViTDet-B 1024^2 k={args.k} workload, fp32 with bf16 "
-                                               f"attention-value path (configs/time/vitdet_vid/_cpu.yml)")
+                                        sample=sample.format(t=r["timed"], k=args.k),
+                                        at_reference_threads=dict(value=round(r8["fps"], 4), cores=r8["cores"],
+                                                                  sample=sample.format(t=r8["timed"], k=args.k)))
     if rank == 0:
         print(json.dumps(line))
     if dist_ctx is not None:

@@ -132,10 +132,57 @@ def test_linear_scatter_epilogue(batch, n, k_sel, kdim, f):
     check(dense.view(-1, f), reference(x, w, b, 0), dtype)
 
 
-def test_linear_rejects_fp32_and_bad_shapes():
+def test_linear_rejects_mixed_dtypes_and_bad_shapes():
     x = torch.zeros(8, 64, device=DEV)
-    with pytest.raises(native.NativeError, match="bf16/fp16"):
-        native.linear(x, torch.zeros(16, 64, device=DEV), None)
+    with pytest.raises(TypeError, match="cast the model or the input"):
+        native.linear(x, torch.zeros(16, 64, device=DEV, dtype=torch.bfloat16), None)
     with pytest.raises(native.NativeError, match="multiples of 8"):
         native.linear(torch.zeros(8, 12, device=DEV, dtype=torch.bfloat16),
                       torch.zeros(16, 12, device=DEV, dtype=torch.bfloat16), None)
+
+
+@pytest.mark.parametrize("m,k,f,act,scatter", [(300, 768, 2304, 0, True), (2048, 768, 3072, 1, True), (512, 3072, 768, 0, True),
+                                               (197, 768, 768, 0, False), (37, 32, 96, 1, True), (1, 128, 4, 0, False)])
+def test_fp32_linear_matches_torch(m, k, f, act, scatter):
+    """fp32 models (BASELINE configs[0]): CUDA-core SGEMM with the same bias / exact-erf GELU / TokenBuffer scatter epilogue."""
+    g = torch.Generator().manual_seed(m + f)
+    x = torch.randn(1, m, k, generator=g)
+    w = torch.randn(f, k, generator=g) / k ** 0.5
+    b = torch.randn(f, generator=g)
+    want = F.linear(x, w, b)
+    if act:
+        want = F.gelu(want)
+    if scatter:
+        n = m + 50
+        idx = torch.randperm(n, generator=g)[:m].view(1, m)
+        buf = torch.full((1, n, f), 7.0)
+        got = native.linear(x.to(DEV), w.to(DEV), b.to(DEV), act=act, out=buf.to(DEV), idx=idx.to(DEV)).cpu()
+        ref = buf.clone()
+        ref[0, idx[0]] = want[0]
+        want = ref
+        count = torch.tensor([m // 2], dtype=torch.int32)  # device-side count: only the first half of the rows is stored
+        got_c = native.linear(x.to(DEV), w.to(DEV), b.to(DEV), act=act, out=buf.to(DEV), idx=idx.to(DEV), count=count.to(DEV)).cpu()
+        ref_c = buf.clone()
+        ref_c[0, idx[0, : m // 2]] = want[0, idx[0, : m // 2]]
+        assert torch.allclose(got_c, ref_c, rtol=2e-5, atol=2e-5)
+    else:
+        got = native.linear(x.to(DEV), w.to(DEV), b.to(DEV), act=act).cpu()
+    assert torch.allclose(got, want, rtol=2e-5, atol=2e-5), float((got - want).abs().max())
+
+
+def test_device_side_count_skips_whole_tiles_on_the_tensor_core_path():
+    """bf16 GEMM with a device-side row count: rows beyond it are neither computed into the buffer nor stored (tiles made only of
+    such rows exit early); rows below it match the un-counted call."""
+    g = torch.Generator().manual_seed(77)
+    m, k, f, n = 1024, 768, 768, 1024
+    x = torch.randn(1, m, k, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(f, k, generator=g) / k ** 0.5).to(torch.bfloat16).to(DEV)
+    b = torch.randn(f, generator=g).to(torch.bfloat16).to(DEV)
+    idx = torch.randperm(n, generator=g)[:m].view(1, m).to(DEV)
+    full = native.linear(x, w, b, out=torch.zeros(1, n, f, dtype=torch.bfloat16, device=DEV), idx=idx)
+    for valid in (0, 1, 130, 517, 1024):
+        count = torch.tensor([valid], dtype=torch.int32, device=DEV)
+        got = native.linear(x, w, b, out=torch.zeros(1, n, f, dtype=torch.bfloat16, device=DEV), idx=idx, count=count)
+        want = torch.zeros_like(full)
+        want[0, idx[0, :valid]] = full[0, idx[0, :valid]]
+        assert torch.equal(got, want), valid

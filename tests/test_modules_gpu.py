@@ -82,7 +82,7 @@ def test_counted_matmul_strided_operands(dtype):
     assert mm.counts["matmul_flops"] == b * h * n * n * dh
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_counted_linear_parts(dtype):
     """forward == forward_linear + bias; forward_bias maps a zero token to the bias (counting.py:127-162)."""
     g = torch.Generator().manual_seed(53)

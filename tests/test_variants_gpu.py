@@ -36,8 +36,9 @@ def test_fp32_free_running_reproduces_the_reference_fixture(name):
     """
     fp32 end to end on the GPU, nothing forced: every frame's output and EVERY gate's selected index set are compared
     with what the unmodified reference produced on the same seeded inputs (tests/golden/*.npz).
-    Index sets must be identical (a token may differ only if its norm ties with the k-th norm to fp32 rounding:
-    at most 0.2 % of a set); outputs within 2e-4 of the output range (5e-3 once a tie has flipped).
+    Measured on B200 (profiles/r2_parity_measured.md): all 505 index sets of the 17 fixtures are IDENTICAL to the
+    reference's, outputs within 2e-6 of the output range.  Asserted: identical sets (a token may differ only if its norm
+    ties with the k-th norm to fp32 rounding: at most 0.2 % of a set) and outputs within 2e-5 (5e-3 once a tie has flipped).
     """
     case, gold = CASES[name], load_golden(name)
     params, frames = case_params(case), case_frames(case)
@@ -64,7 +65,7 @@ def test_fp32_free_running_reproduces_the_reference_fixture(name):
         err = rel_err(got, want)
         record("fp32_vs_reference_fixture", case=name, frame=t, rel_err_of_range=err, exact_sets=exact_sets,
                total_sets=total_sets, worst_overlap=worst_overlap)
-        assert err <= (5e-3 if flipped else 2e-4), f"{name} frame {t}: rel err {err:.2e} (flipped={flipped})"
+        assert err <= (5e-3 if flipped else 2e-5), f"{name} frame {t}: rel err {err:.2e} (flipped={flipped})"
     assert worst_overlap >= 0.998, f"{name}: worst index-set overlap {worst_overlap:.4f}"
     record("fp32_index_sets", case=name, exact_sets=exact_sets, total_sets=total_sets, worst_overlap=worst_overlap)
 
@@ -124,7 +125,7 @@ def test_kv_pooling_and_pool_index(name, dtype):
             got = subsample(outs[t]) if case.get("subsample") else outs[t]
             err = rel_err(got, want)
             record("kv_pooling_fp32_vs_fixture", case=name, frame=t, rel_err_of_range=err)
-            assert err <= 2e-4, f"{name} frame {t}: {err:.2e}"
+            assert err <= 2e-5, f"{name} frame {t}: {err:.2e}"
             for (i, gate), idx in traces[t].items():
                 assert np.array_equal(np.sort(idx.numpy(), axis=-1), gold[f"idx_{t}_{i}_{gate}"]), (t, i, gate)
     else:
@@ -184,4 +185,4 @@ def test_threshold_policy_runs_without_host_sync_and_in_a_cuda_graph(dtype):
             want = oracle.forward(x.clone(), forced=traces[t])
             err = rel_err(eager[t], want)
             record("threshold_device_count", dtype=str(dtype), frame=t, rel_err_of_range=err)
-            assert err <= (2e-4 if dtype == torch.float32 else 4e-2), (t, err)
+            assert err <= (2e-5 if dtype == torch.float32 else 4e-2), (t, err)
