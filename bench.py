@@ -445,7 +445,7 @@ def kernel_leg(streams, n, d, k, grid, pk):
         acc_ms += lib.et_debug_elapsed_ms()
     lib.et_debug_set(6, 0)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     if os.path.exists(tpath) and n == 4096 and k == 2048:
         table = json.load(open(tpath))
         t = table.get("tc_apply_kernel<bf16,DELTA>" if b == 1 else f"tc_apply_kernel<bf16,DELTA>@{b}streams")
@@ -648,7 +648,7 @@ def main():
                                 frac=kt["frac"], traffic=kt.get("traffic"),
                                 peak_source=pk["source"] + ", burst figure (kernel timed alone, L2 flushed, CUDA events "
                                             "on the launch stream)",
-                                traffic_source="ncu --set full, profiles/r1_ncu_traffic.json <- r1_ncu_tc_apply*.csv (dram__bytes_read + write, "
+                                traffic_source="ncu --set full, profiles/r2_ncu_traffic.json <- r2_ncu_tc_apply*.csv (dram__bytes_read + write, "
                                                "one launch at this stream count)",
                                 share_of_step=round(kt["ms"] * kt["per_step"] / (ms / args.steps), 3))
         line["kernels"] = kernels

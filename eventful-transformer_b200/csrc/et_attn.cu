@@ -27,6 +27,10 @@ int et_generic_global_attention(const void* qkv, const void* kv_pooled, int pool
                                 const void* rel_x, int mode, const int64_t* idx, const int32_t* count, int k, void* a_state,
                                 void* v_state, void* acc, void* out, float* stats, void* ws, int B, int N, int gh, int gw,
                                 int H, int dh, int dtype, int state_dtype, cudaStream_t s);
+bool et_tc_window2_applies(int wh, int ww, int dh);
+int et_tc_window2_attention(const void* qkv, const void* pad_token, const void* rel_y, const void* rel_x, void* out, int B, int N,
+                            int gh, int gw, int wh, int ww, int H, int is_bf16, cudaStream_t s);
+int g_attn_win_gen = 2;  // et_debug_set(11, 1) selects the first-generation tcgen05 window kernel (tests compare the two)
 int g_attn_tc = 1;  // et_debug_set(2, 0) forces the mma.sync kernels (tests compare the two paths)
 
 namespace {
@@ -793,7 +797,11 @@ int run_window(const AttnArgs& a, const void* rel_y, const void* rel_x, void* bi
     const int lh = a.windowed ? a.wh : a.gh, lw = a.windowed ? a.ww : a.gw;
     const int nwin = a.windowed ? a.nwx * a.nwy : 1;
     AttnArgs args = a;
-    // tensor-core path: real windows of at most 208 tokens, dh = 64, rel-pos coordinates fitting one 64-column block
+    // second-generation tensor-core path (et_attn_win2_tc.cu): half a window per CTA, two CTAs per SM, rel-pos in the CTA
+    if (a.windowed && g_attn_tc && g_attn_win_gen == 2 && et_tc_window2_applies(a.wh, a.ww, DH))
+        return et_tc_window2_attention(a.qkv, a.pad_token, rel_y, rel_x, a.out, a.B, a.N, a.gh, a.gw, a.wh, a.ww, a.H,
+                                       std::is_same_v<T, __nv_bfloat16> ? 1 : 0, s);
+    // first-generation tensor-core path: real windows of at most 208 tokens, dh = 64, rel-pos coordinates fitting one 64-column block
     if (a.windowed && DH == 64 && a.Wn <= 208 && (rel_y == nullptr || lh + lw <= 32) && g_attn_tc) {
         if (rel_y != nullptr) {
             T* comb = static_cast<T*>(bias_ws);

@@ -600,6 +600,7 @@ int g_force_depth = 0;  // test / tuning hook: et_debug_set(5, 1 = deep pipeline
 }  // namespace
 
 extern int g_attn_tc;
+extern int g_attn_win_gen;
 extern unsigned long long* g_gate_dbg;
 extern int g_tc_time_apply;
 extern unsigned long long* g_tc_prof;
@@ -634,6 +635,10 @@ int et_debug_set(int key, long long value) {
     }
     if (key == 2) {
         g_attn_tc = value != 0;
+        return ET_OK;
+    }
+    if (key == 11) {
+        g_attn_win_gen = value == 1 ? 1 : 2;
         return ET_OK;
     }
     if (key == 7) {

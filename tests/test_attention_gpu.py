@@ -36,6 +36,8 @@ WINDOW_CASES = [  # dim, heads, grid, window, rel size, batch
     (768, 12, (28, 28), (14, 14), (64, 64), 1),   # no padding
     (32, 2, (7, 7), (4, 4), (5, 5), 3),           # dh = 16, padding 7 -> 8
     (64, 2, (9, 5), (3, 5), (4, 4), 2),           # dh = 32, rectangular
+    (128, 2, (11, 7), (5, 3), (5, 3), 2),         # dh = 64, odd window height (uneven halves), padding 11 -> 15, 7 -> 9
+    (128, 2, (16, 16), (16, 16), (16, 16), 1),    # dh = 64, one 256-token window: beyond the tcgen05 window kernels (208 keys)
     (768, 12, (64, 64), (14, 14), (64, 64), 1),   # the benchmarked shape: 1024^2 -> 64 x 64 tokens, 25 windows padded 64 -> 70
 ]
 
@@ -165,19 +167,23 @@ def test_tensor_core_dense_global_attention():
 
 
 @pytest.mark.parametrize("grid,batch", [((16, 16), 2), ((64, 64), 1), ((28, 42), 1)])
-def test_tensor_core_window_path_agrees_with_mma_sync_path(grid, batch):
+def test_tensor_core_window_paths_agree_with_mma_sync_path(grid, batch):
+    """Three implementations of the same function: second- and first-generation tcgen05 window kernels, mma.sync kernel."""
     dim, heads, window = 768, 12, (14, 14)
     params = block_params(dim, heads, window, seed=23, std=0.3)
     qkv = torch.randn(batch, grid[0] * grid[1], 3 * dim, generator=torch.Generator().manual_seed(10)).to(DT).to(DEV)
     outs = []
     try:
-        for flag in (1, 0):
-            native.lib().et_debug_set(2, flag)
+        for tc, gen in ((1, 2), (1, 1), (0, 2)):
+            native.lib().et_debug_set(2, tc)
+            native.lib().et_debug_set(11, gen)
             blk = gpu_block("EventfulTokenwiseBlock", dim, heads, grid, params, rel=(64, 64), window=window)
             outs.append(blk._dense_attention(qkv).clone())
     finally:
         native.lib().et_debug_set(2, 1)
-    assert rel_err(outs[0], outs[1]) < 1.5e-2
+        native.lib().et_debug_set(11, 2)
+    assert rel_err(outs[0], outs[2]) < 1.5e-2
+    assert rel_err(outs[1], outs[2]) < 1.5e-2
 
 
 def test_delta_accumulator_does_not_drift_over_32_frames():
