@@ -239,11 +239,11 @@ def other_configs(device, steps):
             "ViViT-B spatial encoder (K400 shape): 12 views x 197 tokens per step, TopK k=64", VIVIT_B_SPATIAL, (14, 14), 12, device,
             torch.bfloat16, topk(64), steps, has_class_token=True)
         # configs[3]: ViViT-B EPIC-Kitchens shape: 320^2 -> 400 + class token, threshold policy (batch 1, device-side counts)
-        for thr in (0.2, 1.0, 5.0):
+        for thr in (0.2, 1.0, 5.0):  # the reference's threshold sweep values
             out[f"c3_vivit_b_epic_threshold_{thr}"] = side_config(
                 f"ViViT-B spatial encoder (EPIC-Kitchens shape): 1 view x 401 tokens per step, TokenNormThreshold {thr}",
                 VIVIT_B_EPIC, (20, 20), 1, device, torch.bfloat16, (lambda thr=thr: policies.TokenNormThreshold(threshold=thr)),
-                steps, has_class_token=True)
+                steps, has_class_token=True, stream_mode="patch")  # static background + a moving block of changed tokens
     return out
 
 

@@ -35,6 +35,7 @@ using namespace et_tc;
 // et_debug_set(6, 1): bracket the apply-kernel launch with CUDA events on its stream (bench.py reads the elapsed time
 // of the last launch through et_debug_elapsed_ms()); never enabled inside graph capture.
 int g_tc_time_apply = 0;
+int g_tc_apply_cluster = 1;  // et_debug_set(12, n): tc_apply CTAs of n adjacent query blocks form a cluster (experiment)
 // et_debug_set(4, device pointer to 8 x 16 u64): per-role cycle buckets, summed over all CTAs: rows 0-3 tc_apply_kernel
 // (producer, MMA, softmax, mover), rows 4-6 tc_stats_kernel (producer, MMA, softmax).
 // Only the profiling build (make prof: -DET_TC_PROFILE -> libeventful_b200_prof.so) writes to it.
@@ -729,7 +730,8 @@ int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, i
     }
     if (mode == ET_ATTN_DELTA) {
         if ((rc = make_tmap_2d(&tmsel, sel, 3LL * a.sel_rows, (long long)a.D, 64, a.is_bf16))) return rc;
-        et_launch(tc_apply_kernel<BF16, ET_ATTN_DELTA>, dim3(grid), dim3(kApThreads), AP_SMEM, s, tm128, tmsel, tmbh, tmbw, tmoh, a);
+        const int cl = (g_tc_apply_cluster > 1 && grid.x % g_tc_apply_cluster == 0) ? g_tc_apply_cluster : 1;
+        et_launch_cluster(tc_apply_kernel<BF16, ET_ATTN_DELTA>, dim3(grid), dim3(kApThreads), AP_SMEM, s, cl, tm128, tmsel, tmbh, tmbw, tmoh, a);
     } else if (mode == ET_ATTN_FIRST) {
         et_launch(tc_apply_kernel<BF16, ET_ATTN_FIRST>, dim3(grid), dim3(kApThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
     } else {

@@ -222,6 +222,27 @@ int et_raise_smem_impl(const void* kernel, int bytes);
 template <typename K>
 inline int et_raise_smem(K kernel, int bytes) { return et_raise_smem_impl(reinterpret_cast<const void*>(kernel), bytes); }
 
+// As et_launch, with the CTAs grouped into thread-block clusters of `cluster_x` along grid.x (co-scheduled on one GPC).
+template <typename... KArgs, typename... Args>
+inline void et_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_et_pdl;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster_x;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cluster_x > 1 ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Number of kernels this library has enqueued (bench.py reports it as gpu_launches).
 extern long long g_et_launches;
 #define ET_COUNT_LAUNCH(n) (g_et_launches += (n))

@@ -601,6 +601,7 @@ int g_force_depth = 0;  // test / tuning hook: et_debug_set(5, 1 = deep pipeline
 
 extern int g_attn_tc;
 extern int g_attn_win_gen;
+extern int g_tc_apply_cluster;
 extern unsigned long long* g_gate_dbg;
 extern int g_tc_time_apply;
 extern unsigned long long* g_tc_prof;
@@ -635,6 +636,10 @@ int et_debug_set(int key, long long value) {
     }
     if (key == 2) {
         g_attn_tc = value != 0;
+        return ET_OK;
+    }
+    if (key == 12) {
+        g_tc_apply_cluster = value >= 1 && value <= 8 ? (int)value : 1;
         return ET_OK;
     }
     if (key == 11) {

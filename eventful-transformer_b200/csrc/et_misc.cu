@@ -96,3 +96,48 @@ extern "C" int et_bmm(const void* A, const void* Bm, void* C, int64_t batch_oute
     ET_CHECK_LAUNCH("et_bmm");
     return ET_OK;
 }
+
+// ---------------------------------------------------------------- patch / tubelet extraction for the embedding GEMM
+// LinearEmbedding (models/vitdet.py:17-52: Conv2d with kernel = stride = patch) and TubeletEmbedding (models/vivit.py:
+// 153-192: Conv3d with kernel = stride = tubelet) are GEMMs over non-overlapping patches.  This kernel lays the patches out
+// as rows -- out[b, t', n, (c, dt, dy, dx)] = x[b, t' pt + dt, c, y ph + dy, x pw + dx], the order of the flattened conv
+// weight (dim, C, pt, ph, pw) -- so that the projection itself runs on et_linear.
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_kernel(const T* x, T* out, int Tn, int C, int H, int W, int pt, int ph, int pw,
+                                                       long long total) {
+    et_pdl_prologue();
+    const int gw = W / pw, gh = H / ph, tn = Tn / pt;
+    const int F = C * pt * ph * pw;
+    for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < total; gi += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(gi % F);
+        long long r = gi / F;
+        const int n = (int)(r % (gh * gw));
+        r /= gh * gw;
+        const int tt = (int)(r % tn);
+        const long long b = r / tn;
+        const int dx = f % pw, dy = (f / pw) % ph, dt = (f / (pw * ph)) % pt, c = f / (pw * ph * pt);
+        const int py = n / gw, px = n - py * gw;
+        out[gi] = x[(((b * Tn + (long long)tt * pt + dt) * C + c) * H + py * ph + dy) * W + px * pw + dx];
+    }
+}
+}  // namespace
+
+extern "C" int et_patchify(const void* x, void* out, int64_t B, int64_t T, int64_t C, int64_t H, int64_t W, int64_t pt, int64_t ph,
+                           int64_t pw, int dtype, void* stream) {
+    ET_CHECK_ARG(x && out, "et_patchify: null pointer");
+    ET_CHECK_ARG(pt > 0 && ph > 0 && pw > 0 && T % pt == 0 && H % ph == 0 && W % pw == 0,
+                 "et_patchify: input (%lld, %lld, %lld) is not a multiple of the patch (%lld, %lld, %lld)", (long long)T, (long long)H,
+                 (long long)W, (long long)pt, (long long)ph, (long long)pw);
+    const long long total = (long long)B * T * C * H * W;
+    if (total == 0) return ET_OK;
+    const long long blocks = (total + 255) / 256, cap = (long long)et_sm_count() * 16;
+    const dim3 grid((unsigned)(blocks > cap ? cap : blocks));
+    ET_DISPATCH_DTYPE(dtype, Tp, {
+        et_launch(patchify_kernel<Tp>, grid, dim3(256), 0, et_stream(stream), static_cast<const Tp*>(x), static_cast<Tp*>(out), (int)T, (int)C,
+                  (int)H, (int)W, (int)pt, (int)ph, (int)pw, total);
+    });
+    ET_COUNT_LAUNCH(1);
+    ET_CHECK_LAUNCH("et_patchify");
+    return ET_OK;
+}

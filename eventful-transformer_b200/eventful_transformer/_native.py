@@ -50,6 +50,7 @@ _SIGNATURES = {
     "et_global_attention": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                     c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                     c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "et_patchify": (c_int, [c_void_p, c_void_p] + [c_int64] * 8 + [c_int, c_void_p]),
     "et_pool_kv": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "et_pool_index": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
                               c_void_p, c_void_p]),
@@ -411,4 +412,23 @@ def bmm(a, b, out=None, accumulate=False, alpha=1.0):
     arr = lambda t: (c_int64 * 4)(*t.stride())  # noqa: E731
     _check(lib().et_bmm(_p(a4), _p(b4), _p(o4), o4.shape[0], o4.shape[1], m, n, kd, arr(a4), arr(b4), arr(o4),
                         int(accumulate), float(alpha), dtype_code(a), _stream()), "et_bmm")
+    return out
+
+
+def patchify(x, patch):
+    """
+    Non-overlapping patches / tubelets as GEMM rows.  x (B, C, H, W) with patch (ph, pw), or x (B, T, C, H, W) with patch
+    (pt, ph, pw)  ->  (B, N, C*ph*pw) or (B, T/pt, N, C*pt*ph*pw), features in the order of the flattened conv weight.
+    """
+    require_device(x)
+    _dense(x, "image / video")
+    if x.dim() == 4:
+        (b, c, h, w), t = x.shape, 1
+        pt, (ph, pw) = 1, patch
+    else:
+        b, t, c, h, w = x.shape
+        pt, ph, pw = patch
+    n, f = (h // ph) * (w // pw), c * pt * ph * pw
+    out = torch.empty((b, n, f) if x.dim() == 4 else (b, t // pt, n, f), dtype=x.dtype, device=x.device)
+    _check(lib().et_patchify(_p(x), _p(out), b, t, c, h, w, pt, ph, pw, dtype_code(x), _stream()), "et_patchify")
     return out

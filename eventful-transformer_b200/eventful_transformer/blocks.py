@@ -65,6 +65,8 @@ class Block(ExtendedModule):
         super().__init__()
         self.heads = heads
         self.input_size = tuple(input_size)
+        # token grid handed to the attention kernels: (h, w), or (1, t) for 1-D inputs (ViViT's temporal sub-model)
+        self._grid = self.input_size if len(self.input_size) == 2 else (1, prod(self.input_size))
         self._identity = {}
         if ats_fraction is not None:
             assert pool_size is None
@@ -164,7 +166,7 @@ class Block(ExtendedModule):
 
     def _window_grid(self):
         wh, ww = self.window_size
-        gh, gw = self.input_size
+        gh, gw = self._grid
         th, tw = gh + (-gh % wh), gw + (-gw % ww)
         return (th // wh) * (tw // ww), (th, tw) != (gh, gw)
 
@@ -176,7 +178,7 @@ class Block(ExtendedModule):
         if self.window_size is not None:
             n_win, padded = self._window_grid()
             w2 = prod(self.window_size)
-            out = native.window_attention(qkv, self.heads, self.input_size, self.window_size,
+            out = native.window_attention(qkv, self.heads, self._grid, self.window_size,
                                           pad_token=self.qkv.bias.detach(), rel=rel)
             if self.count_mode:
                 if padded:
@@ -190,14 +192,14 @@ class Block(ExtendedModule):
         if self.pool_size is not None or sdt != qkv.dtype:
             kvp = None
             if self.pool_size is not None:
-                kvp = native.pool_kv(qkv, self.input_size, self.pool_size)
+                kvp = native.pool_kv(qkv, self._grid, self.pool_size)
                 n_keys = kvp.shape[1]
-            out = native.global_attention(qkv, self.heads, self.input_size, native.ATTN_DENSE, rel=rel, kv_pooled=kvp,
+            out = native.global_attention(qkv, self.heads, self._grid, native.ATTN_DENSE, rel=rel, kv_pooled=kvp,
                                           pool=self.pool_size, state_dtype=sdt)
         elif n <= _SMALL_ATTENTION:
-            out = native.window_attention(qkv, self.heads, self.input_size, None, rel=rel)
+            out = native.window_attention(qkv, self.heads, self._grid, None, rel=rel)
         else:
-            out = native.global_attention(qkv, self.heads, self.input_size, native.ATTN_DENSE, rel=rel)
+            out = native.global_attention(qkv, self.heads, self._grid, native.ATTN_DENSE, rel=rel)
         if self.count_mode:
             self.matmul.counts["matmul_flops"] += 2 * b * self.heads * n * n_keys * dh
             if rel is not None:
@@ -365,7 +367,7 @@ class EventfulMatmul1Block(EventfulTokenwiseBlock):
         h, dh = self.heads, self.dim // self.heads
         q = qkv[..., : self.dim].reshape(b, n, h, dh).permute(0, 2, 1, 3)
         if self.pool_size is not None:
-            kv = native.pool_kv(qkv, self.input_size, self.pool_size)
+            kv = native.pool_kv(qkv, self._grid, self.pool_size)
             keys = kv[..., : self.dim].reshape(b, kv.shape[1], h, dh).permute(0, 2, 3, 1)
         else:
             keys = qkv[..., self.dim: 2 * self.dim].reshape(b, n, h, dh).permute(0, 2, 3, 1)
@@ -375,10 +377,10 @@ class EventfulMatmul1Block(EventfulTokenwiseBlock):
         """(pooled [k | v] tensor, pooled index, its device-side count) -- or (None, index, count) without pooling."""
         if self.pool_size is None:
             return None, index, count
-        kvp = native.pool_kv(qkv, self.input_size, self.pool_size)
+        kvp = native.pool_kv(qkv, self._grid, self.pool_size)
         if index is None:
             return kvp, None, None
-        index_k, count_k = native.pool_index(index, count, self.input_size, self.pool_size)  # blocks.py:525-540
+        index_k, count_k = native.pool_index(index, count, self._grid, self.pool_size)  # blocks.py:525-540
         return kvp, index_k, count_k
 
     def _count_matmul_1(self, qkv, n_keys, rows_q, cols_k):
@@ -395,7 +397,7 @@ class EventfulMatmul1Block(EventfulTokenwiseBlock):
                 self.relative_position.count_fused(b * self.heads, n, n_keys)
 
     def _global(self, qkv, mode, **kw):
-        return native.global_attention(qkv, self.heads, self.input_size, mode, rel=self._rel_tables(qkv.dtype),
+        return native.global_attention(qkv, self.heads, self._grid, mode, rel=self._rel_tables(qkv.dtype),
                                        pool=self.pool_size, state_dtype=self._state_dtype(qkv.dtype), **kw)
 
     def _attention_first(self, qkv, index):

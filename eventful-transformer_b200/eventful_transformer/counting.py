@@ -109,9 +109,26 @@ class CountedLinear(_Counted):
             self._tally("bias_flops", n_rows * self.out_features)
         self._tally("linear_flops", n_rows * self.in_features * self.out_features)
 
+    def _padded_parameters(self):
+        """16-bit GEMM tiles store 16-byte vectors: an odd feature count (e.g. a 97-class head) runs on zero-padded copies."""
+        w, b = self.weight.detach(), self.bias.detach()
+        key = (w.data_ptr(), w._version, b._version, w.dtype)
+        if getattr(self, "_pad_key", None) != key:
+            f = (self.out_features + 7) // 8 * 8
+            wp = torch.zeros((f, self.in_features), dtype=w.dtype, device=w.device)
+            bp = torch.zeros((f,), dtype=b.dtype, device=b.device)
+            wp[: self.out_features].copy_(w)
+            bp[: self.out_features].copy_(b)
+            self._pad_key, self._pad = key, (wp, bp)
+        return self._pad
+
     def forward(self, x, act=native.ACT_NONE, out=None, idx=None, count=None, rows=None):
         """`count`: device-side number of valid rows per batch entry; `rows`: their host-side total for the counters."""
-        y = native.linear(x.contiguous(), self.weight.detach(), self.bias.detach(), act=act, out=out, idx=idx, count=count)
+        if self.out_features % 8 and self.weight.dtype != torch.float32 and out is None and idx is None:
+            wp, bp = self._padded_parameters()
+            y = native.linear(x.contiguous(), wp, bp, act=act)[..., : self.out_features]
+        else:
+            y = native.linear(x.contiguous(), self.weight.detach(), self.bias.detach(), act=act, out=out, idx=idx, count=count)
         self.count_linear(x.numel() // self.in_features if rows is None else rows)
         return y
 

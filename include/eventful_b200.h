@@ -101,7 +101,8 @@ int et_sub(const void* a, const void* b, void* out, int64_t n, int dtype, void* 
  * 2 shallow = two CTAs per SM, 0 = automatic); key 6: 1 brackets the global-attention apply kernel with CUDA events;
  * key 4 / key 7: device pointer to 8 x 16 / 3 x 16 uint64 cycle buckets per warp role of the attention / GEMM kernels
  * (written only by the profiling build, `make prof`); key 8: GEMM rows per CTA tile (1 = 128, 2 = 256, 0 = automatic);
- * key 9: persistent GEMM kernel (1 = always, 2 = never, 0 = automatic); key 10: CTAs per SM of the gate kernels (default 2). */
+ * key 9: persistent GEMM kernel (1 = always, 2 = never, 0 = automatic); key 10: CTAs per SM of the gate kernels (default 2);
+ * key 11: 1 selects the first-generation tcgen05 window-attention kernel (default 2 = second generation). */
 int et_debug_set(int key, long long value);
 /* Milliseconds of the last apply-kernel launch bracketed under key 6 (synchronises on its end event). */
 float et_debug_elapsed_ms(void);
@@ -200,6 +201,15 @@ int et_pool_index(const int64_t* idx, const int32_t* count_in, int64_t B, int64_
 int et_bmm(const void* A, const void* Bm, void* C, int64_t batch_outer, int64_t batch_inner, int64_t M, int64_t N,
            int64_t K, const int64_t* strides_a, const int64_t* strides_b, const int64_t* strides_c, int accumulate,
            float alpha, int dtype, void* stream);
+
+/*
+ * Patch / tubelet extraction for the embedding GEMM: LinearEmbedding (models/vitdet.py:17-52, Conv2d with
+ * kernel = stride = patch) and TubeletEmbedding (models/vivit.py:153-192, Conv3d with kernel = stride = tubelet) are GEMMs
+ * over non-overlapping patches.  x (B, T, C, H, W) [T = pt = 1 for images] -> out (B, T/pt, (H/ph)(W/pw), C*pt*ph*pw) with
+ * the feature order of the flattened conv weight (dim, C, pt, ph, pw); the projection then runs on et_linear.
+ */
+int et_patchify(const void* x, void* out, int64_t B, int64_t T, int64_t C, int64_t H, int64_t W, int64_t pt, int64_t ph,
+                int64_t pw, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

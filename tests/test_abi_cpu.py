@@ -140,3 +140,55 @@ def test_reference_models_construct_on_top_of_this_package():
         sys.path.remove(REFERENCE)
         for mod in [m for m in sys.modules if m == "models" or m.startswith("models.") or m == "utils" or m.startswith("utils.")]:
             sys.modules.pop(mod, None)
+
+
+def test_model_ends_keep_the_reference_state_dict_keys():
+    """et_models.FactorizedViViT / ViTDetStem expose exactly the parameter names the reference models have (the fixtures store
+    the reference's own state dicts), so converted checkpoints load unchanged."""
+    import numpy as np
+
+    import et_models
+    from golden_util import GOLDEN_DIR
+    from model_cases import VITDET_STEM_TINY, VIVIT_TINY
+
+    gold = np.load(os.path.join(GOLDEN_DIR, "model_vivit_tiny.npz"))
+    want = {k[len("param/"):]: gold[k].shape for k in gold.files if k.startswith("param/")}
+    model = et_models.FactorizedViViT(**VIVIT_TINY["model"])
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == want
+    assert model.temporal_model.backbone.blocks[0]._grid == (1, 4)  # 1-D token axis of the temporal sub-model
+    gold = np.load(os.path.join(GOLDEN_DIR, "model_vitdet_stem_tiny.npz"))
+    want = {k[len("param/"):]: gold[k].shape for k in gold.files if k.startswith("param/")}
+    cfg = VITDET_STEM_TINY
+    stem = et_models.ViTDetStem(cfg["backbone_config"], cfg["input_shape"], cfg["normalize_mean"], cfg["normalize_std"],
+                                cfg["patch_size"])
+    assert {k: tuple(v.shape) for k, v in stem.state_dict().items()} == want
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree only exists in the build container")
+def test_reference_vitdet_stem_constructs_on_top_of_this_package():
+    """models/vitdet.py of the reference (detectron2 stubbed: not installed) builds its embedding + backbone on this package."""
+    stubs = ("matplotlib", "matplotlib.pyplot", "detectron2", "detectron2.config", "detectron2.structures")
+    added = [name for name in stubs if name not in sys.modules]
+    for name in added:
+        sys.modules[name] = types.ModuleType(name)
+    if "detectron2.config" in added:
+        sys.modules["detectron2.config"].LazyConfig = object
+        sys.modules["detectron2.config"].instantiate = lambda *a, **k: None
+        sys.modules["detectron2.structures"].ImageList = object
+    sys.path.append(REFERENCE)
+    try:
+        import importlib
+
+        vitdet = importlib.import_module("models.vitdet")
+        assert vitdet.ViTBackbone is backbones.ViTBackbone
+        emb = vitdet.LinearEmbedding(3, 768, (16, 16))
+        assert emb.conv.weight.shape == (768, 3, 16, 16)
+        bb = vitdet.ViTBackbone(input_size=(64, 64), **syn.backbone_kwargs(syn.VITDET_B, (64, 64)).__class__(
+            {k: v for k, v in syn.backbone_kwargs(syn.VITDET_B, (64, 64)).items() if k != "input_size"}))
+        assert len(bb.blocks) == 12
+    finally:
+        sys.path.remove(REFERENCE)
+        for mod in [m for m in sys.modules if m == "models" or m.startswith("models.") or m == "utils" or m.startswith("utils.")]:
+            sys.modules.pop(mod, None)
+        for name in added:
+            sys.modules.pop(name, None)
