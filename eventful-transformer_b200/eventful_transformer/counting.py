@@ -103,6 +103,9 @@ class CountedLinear(_Counted):
         self.weight = _zeros_parameter((out_features, in_features), device, dtype)
         self.bias = _zeros_parameter(out_features, device, dtype)
 
+    def reset_self(self):
+        self._pad_key = self._pad = None
+
     def count_linear(self, n_rows, with_bias=True):
         """Counters of this layer applied to n_rows rows (the fused block path calls the GEMM directly)."""
         if with_bias:
@@ -112,7 +115,7 @@ class CountedLinear(_Counted):
     def _padded_parameters(self):
         """16-bit GEMM tiles store 16-byte vectors: an odd feature count (e.g. a 97-class head) runs on zero-padded copies."""
         w, b = self.weight.detach(), self.bias.detach()
-        key = (w.data_ptr(), w._version, b._version, w.dtype)
+        key = (w.data_ptr(), b.data_ptr(), w.dtype, w.device)  # dropped by reset(), like the other cached tables
         if getattr(self, "_pad_key", None) != key:
             f = (self.out_features + 7) // 8 * 8
             wp = torch.zeros((f, self.in_features), dtype=w.dtype, device=w.device)
