@@ -290,8 +290,16 @@ __global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_co
 }
 
 // ============================================================================================= phase B
-constexpr int kMoverWarps = 8;                        // warps 2-3 and 12 .. 12 + kMoverWarps - 3
-constexpr int kApThreads = (10 + kMoverWarps) * 32;  // warp 0 TMA, 1 MMA, 4-11 softmax, the rest state movers
+// State-mover warps of tc_apply: 8 = warps 2-3 and 12-17 (576 threads); 16 = warps 12-27 (896 threads, warps 2-3 idle), with
+// the register file re-divided by setmaxnreg (softmax warpgroups 104, everything else 40 / 56) -- build-time experiment switch.
+#ifndef ET_APPLY_MOVERS
+#define ET_APPLY_MOVERS 8
+#endif
+constexpr int kMoverWarps = ET_APPLY_MOVERS;
+constexpr bool kWideMovers = kMoverWarps > 8;
+constexpr int kApThreads = kWideMovers ? (12 + kMoverWarps) * 32 : (10 + kMoverWarps) * 32;  // warp 0 TMA, 1 MMA, 4-11 softmax
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int MV_CPT = 1024 / (kMoverWarps * 32);    // 16-byte chunks per mover thread and tile
 constexpr int MV_CSTEP = kMoverWarps * 2;            // columns covered by one pass of the mover threads
 constexpr int AP_KEYS = 64;
@@ -304,7 +312,10 @@ constexpr int AP_OFF_PT = AP_OFF_ST + 2 * AP_STAGE;
 constexpr int AP_PT_STAGES = 4;                   // a_state tiles are prefetched four tiles ahead by the mover warps
 constexpr int AP_OFF_P = AP_OFF_PT + AP_PT_STAGES * AP_PT;
 constexpr int AP_OFF_MISC = AP_OFF_P + AP_P;
-constexpr int AP_SMEM = AP_OFF_MISC + 1024 + 1024;
+constexpr int AP_OFF_IDX = AP_OFF_MISC + 1024;    // int32 copy of this batch entry's selected-key index (DELTA mode, k <= AP_IDX_MAX)
+constexpr int AP_IDX_MAX = 3584;                  // 14 KB: what is left of the 227 KB
+constexpr int AP_SMEM = AP_OFF_IDX + AP_IDX_MAX * 4 + 1024;
+static_assert(AP_SMEM <= 227 * 1024, "tc_apply shared memory");
 
 template <bool BF16, int MODE>
 __global__ void __launch_bounds__(kApThreads, 1)
@@ -315,9 +326,12 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     auto Qb = [&](int i) { return smem + i * QROWS * 128; };
-    auto Kb = [&](int u, int i) { return smem + AP_OFF_ST + u * AP_STAGE + i * AP_BLK; };  // 0 k, 1 oh-y, 2 oh-x
-    auto V1 = [&](int u) { return smem + AP_OFF_ST + u * AP_STAGE + 3 * AP_BLK; };
-    auto V2 = [&](int u) { return smem + AP_OFF_ST + u * AP_STAGE + 4 * AP_BLK; };
+    // K' blocks (i = 0 k, 1 onehot-y, 2 onehot-x) of the two 64-key tiles u = 0, 1 of a PAIR sit next to each other, so that one
+    // N = 128 MMA covers both tiles: a tcgen05.mma costs ~90 cycles whether N is 64 or 128 (profiles/r1_mma_rate_microbench.txt),
+    // and S' was 12 of the 20 MMAs per tile.  V blocks keep a two-deep ring per 64-key tile.
+    auto Kb = [&](int u, int i) { return smem + AP_OFF_ST + (2 * i + u) * AP_BLK; };
+    auto V1 = [&](int u) { return smem + AP_OFF_ST + (6 + 2 * u) * AP_BLK; };
+    auto V2 = [&](int u) { return smem + AP_OFF_ST + (7 + 2 * u) * AP_BLK; };
     // MN-major A tiles [64 keys][128 rows]: two 8 KB blocks of 64 rows; key kk = one 128-byte line per block,
     // its 16-byte chunk c (8 rows) stored at chunk position c ^ (kk & 7)
     auto Pt = [&](int u) { return smem + AP_OFF_PT + u * AP_PT; };
@@ -325,7 +339,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     auto a_chunk = [](int key, int seg) { return (seg >> 3) * 8192 + key * 128 + (((seg & 7) ^ (key & 7)) << 4); };
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AP_OFF_MISC + 512);
     uint64_t* q_full = bars;
-    uint64_t* k_full = bars + 1;    // [2]: K' operand blocks of a stage landed
+    uint64_t* k_full = bars + 1;    // [0]: K' operand blocks of a tile pair landed
     uint64_t* ps_full = bars + 3;   // [4]: a_state tile landed (128 cp.async arrivals, one per mover thread)
     uint64_t* s_full = bars + 7;
     uint64_t* s_empty = bars + 9;
@@ -334,7 +348,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint64_t* o_full = bars + 14;
     uint64_t* an_free = bars + 15;  // a_n tile copied out by the 4 mover warps, one phase per tile
     uint64_t* v_full = bars + 16;   // [2]: V blocks of a stage landed (released by pv_done)
-    uint64_t* k_empty = bars + 18;  // [2]: S' MMAs of the stage's tile are complete -> its K' blocks may be reloaded
+    uint64_t* k_empty = bars + 18;  // [0]: S' MMAs of the pair are complete -> the K' blocks may be reloaded
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -357,135 +371,19 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_init(smem_u32(&v_full[u]), 1);
             mbar_init(smem_u32(&k_empty[u]), 1);
             mbar_init(smem_u32(&s_full[u]), 1);
-            mbar_init(smem_u32(&s_empty[u]), 8);
+            mbar_init(smem_u32(&s_empty[u]), 16);  // a pair buffer is drained by 8 softmax warps x 2 tiles
             mbar_init(smem_u32(&pv_done[u]), 1);
         }
         for (int u = 0; u < AP_PT_STAGES; ++u) mbar_init(smem_u32(&ps_full[u]), kMoverWarps * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);  // S' pair buffers 2 x 128 columns, O 64 columns
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_o = tmem_base + 2 * AP_KEYS;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ producer + state write-back
-        if (lane == 0) {
-            const int qrow = b * a.N + q0;
-            mbar_expect_tx(smem_u32(q_full), nkb * QROWS * 128);
-            tma_load_2d(smem_u32(Qb(0)), &tm_q, smem_u32(q_full), h * 64, qrow);
-            if (a.has_bias) {
-                const int brow = (b * a.H + h) * a.N + q0;
-                tma_load_2d(smem_u32(Qb(1)), &tm_bh, smem_u32(q_full), 0, brow);
-                tma_load_2d(smem_u32(Qb(2)), &tm_bw, smem_u32(q_full), 0, brow);
-            }
-        }
-        // K' blocks and V blocks of a stage are separate transactions: K'(t) is reloadable as soon as S'(t-2) has been
-        // computed (a full tile before the PV MMAs of t-2 finish), so the S' MMAs - which run one tile ahead of the PV
-        // MMAs - never wait for the TMA round trip.  Issue order: K'(0) K'(1) V(0) K'(2) V(1) ...
-        PF_DECL
-        if (lane == 0) {
-            for (int i = 0; i <= T; ++i) {
-                if (i < T) {
-                    const int u = i & 1, key0 = i * AP_KEYS;
-                    PF(1);
-                    if (i >= 2) mbar_wait(smem_u32(&k_empty[u]), ((i >> 1) & 1) ^ 1);
-                    PF(0);
-                    const uint32_t fb = smem_u32(&k_full[u]);
-                    mbar_expect_tx(fb, nkb * AP_BLK);
-                    if (MODE == ET_ATTN_DELTA) tma_load_2d(smem_u32(Kb(u, 0)), &tm_kv, fb, h * 64, b * a.k + key0);
-                    else tma_load_2d(smem_u32(Kb(u, 0)), &tm_kv, fb, a.D + h * 64, b * a.N + key0);
-                    if (a.has_bias) {
-                        const int orow = (MODE == ET_ATTN_DELTA) ? b * a.k + key0 : key0;
-                        tma_load_2d(smem_u32(Kb(u, 1)), &tm_oh, fb, 0, orow);
-                        tma_load_2d(smem_u32(Kb(u, 2)), &tm_oh, fb, 64, orow);
-                    }
-                }
-                if (i >= 1) {
-                    const int j = i - 1, u = j & 1, key0 = j * AP_KEYS;
-                    PF(1);
-                    if (j >= 2) mbar_wait(smem_u32(&pv_done[u]), ((j >> 1) & 1) ^ 1);  // tile j-2: the PV MMAs are done with slot u
-                    PF(2);
-                    const uint32_t fb = smem_u32(&v_full[u]);
-                    mbar_expect_tx(fb, (MODE == ET_ATTN_DELTA ? 2 : 1) * AP_BLK);
-                    if (MODE == ET_ATTN_DELTA) {
-                        const int r0 = b * a.k + key0;
-                        tma_load_2d(smem_u32(V1(u)), &tm_kv, fb, h * 64, a.sel_rows + r0);
-                        tma_load_2d(smem_u32(V2(u)), &tm_kv, fb, h * 64, 2 * a.sel_rows + r0);
-                    } else {
-                        tma_load_2d(smem_u32(V1(u)), &tm_kv, fb, 2 * a.D + h * 64, b * a.N + key0);
-                    }
-                }
-            }
-        }
-        PF(1);
-        if (lane == 0) PF_FLUSH(0);
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc_s = umma_idesc_ex(128, AP_KEYS, a.is_bf16, 0);
-            // PV products: A = [key][row] tiles (MN-major), B = V tiles (MN-major); the p . Vd product is subtracted
-            const uint32_t idesc_o = umma_idesc_ex(128, 64, a.is_bf16, 1) | (1u << 15);
-            const uint32_t idesc_neg = idesc_o | (1u << 13);  // a_negate
-            PF_DECL
-            mbar_wait(smem_u32(q_full), 0);
-            PF(7);
-            auto issue_s = [&](int t) {
-                const int u = t & 1;
-                mbar_wait(smem_u32(&k_full[u]), (t >> 1) & 1);
-                PF(0);
-                mbar_wait(smem_u32(&s_empty[u]), ((t >> 1) & 1) ^ 1);
-                PF(1);
-                tcgen05_fence_after();
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const uint64_t dq = umma_smem_desc(smem_u32(Qb(kb)));
-                    const uint64_t dk = umma_smem_desc(smem_u32(Kb(u, kb)));
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        tcgen05_mma_f16(tmem_base + u * AP_KEYS, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s,
-                                        (kb > 0 || kk > 0));
-                }
-                tcgen05_commit(smem_u32(&s_full[u]));
-                tcgen05_commit(smem_u32(&k_empty[u]));
-                PF(2);
-            };
-            auto issue_pv = [&](int t) {
-                const int u = t & 1;
-                mbar_wait(smem_u32(p_ready), t & 1);
-                PF(3);
-                mbar_wait(smem_u32(&v_full[u]), (t >> 1) & 1);
-                PF(8);
-                tcgen05_fence_after();
-                const uint64_t dan = umma_smem_desc_mn_a(smem_u32(An));
-                const uint64_t dv1 = umma_smem_desc_mn(smem_u32(V1(u)));
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)  // 16 keys per step = 16 lines of 128 B (2048 B) in the A and V tiles
-                    tcgen05_mma_f16(tmem_o, dan + (uint64_t)(128 * kk), dv1 + (uint64_t)(128 * kk), idesc_o, (t > 0 || kk > 0));
-                PF(4);
-                if (MODE == ET_ATTN_DELTA) {
-                    mbar_wait(smem_u32(&ps_full[t % AP_PT_STAGES]), (t / AP_PT_STAGES) & 1);  // old state tile landed
-                    PF(5);
-                    fence_proxy_async();  // cp.async (generic proxy) writes -> visible to the tensor core
-                    const uint64_t dp = umma_smem_desc_mn_a(smem_u32(Pt(t % AP_PT_STAGES)));
-                    const uint64_t dv2 = umma_smem_desc_mn(smem_u32(V2(u)));
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        tcgen05_mma_f16(tmem_o, dp + (uint64_t)(128 * kk), dv2 + (uint64_t)(128 * kk), idesc_neg, 1u);
-                }
-                tcgen05_commit(smem_u32(&pv_done[u]));
-                if (t == T - 1) tcgen05_commit(smem_u32(o_full));
-                PF(6);
-            };
-            if (T > 0) issue_s(0);
-            for (int t = 0; t < T; ++t) {
-                if (t + 1 < T) issue_s(t + 1);
-                issue_pv(t);
-            }
-            PF_FLUSH(1);
-        }
-    } else if (warp < 4 || warp >= 12) {
+    const uint32_t tmem_o = tmem_base + 4 * AP_KEYS;
+    auto state_movers = [&]() {
         // ------------------------------------------------------------------ A-gate state movers
         // A selected column x this CTA's 128 rows is 256 contiguous bytes of the column-major state = 16 threads x 16 B;
         // thread mt moves segment (mt & 15) of columns (mt >> 4) + MV_CSTEP i, i < MV_CPT.  Per tile: prefetch the old state tile
@@ -493,12 +391,21 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // (modules.py:200).  Scattered 256-byte HBM segments stall the issuing warps (LSU back-pressure), so this traffic
         // has its own warps and never holds up the exp / MMA pipeline.
         if (MODE != ET_ATTN_DENSE) {
-            const int mt = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
+            const int mt = (kWideMovers ? warp - 12 : (warp < 4 ? warp - 2 : warp - 10)) * 32 + lane;
             const int segi = mt & 15, seg = segi * 8, col0 = mt >> 4;
+            // the index of this batch entry goes to shared memory once: every tile needs it twice per thread (prefetch and
+            // write-back), and an L2 round trip per tile was 15 % of the movers' time (profiles/r1_tc_apply_roles.txt)
+            int* s_idx = reinterpret_cast<int*>(smem + AP_OFF_IDX);
+            const bool idx_in_smem = MODE == ET_ATTN_DELTA && nkeys <= AP_IDX_MAX;
+            if (idx_in_smem) {
+                for (int j = mt; j < nkeys; j += kMoverWarps * 32) s_idx[j] = (int)a.idx[(size_t)b * a.k + j];
+                asm volatile("bar.sync 2, %0;" ::"n"(kMoverWarps * 32) : "memory");
+            }
             auto tile_tok = [&](int tt, int i) -> int {  // token of column col0 + 8 i of tile tt (or -1)
                 const int j = tt * AP_KEYS + col0 + MV_CSTEP * i;
                 if (j >= nkeys) return -1;
-                return (MODE == ET_ATTN_DELTA) ? (int)a.idx[(size_t)b * a.k + j] : j;
+                if (MODE != ET_ATTN_DELTA) return j;
+                return idx_in_smem ? s_idx[j] : (int)a.idx[(size_t)b * a.k + j];
             };
             auto load_state = [&](int tt, const int (&tok)[MV_CPT]) {  // a_state[:, idx of tile tt] -> Pt ring (A-operand layout)
                 uint8_t* dst = Pt(tt % AP_PT_STAGES);
@@ -554,8 +461,136 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             if (warp == 2 && lane == 0) PF_FLUSH(3);
         }
-    } else {
+    };
+
+    // Role dispatch by warpgroup, so that each setmaxnreg (16-mover build) is executed by the four warps of a warpgroup together
+    // and dominates the code it budgets: 0 = TMA / MMA (/ movers in the 8-mover build), 1-2 = softmax, 3+ = movers.
+    if (kWideMovers && warp < 4) setmaxnreg_dec<40>();
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer + state write-back
+        if (lane == 0) {
+            const int qrow = b * a.N + q0;
+            mbar_expect_tx(smem_u32(q_full), nkb * QROWS * 128);
+            tma_load_2d(smem_u32(Qb(0)), &tm_q, smem_u32(q_full), h * 64, qrow);
+            if (a.has_bias) {
+                const int brow = (b * a.H + h) * a.N + q0;
+                tma_load_2d(smem_u32(Qb(1)), &tm_bh, smem_u32(q_full), 0, brow);
+                tma_load_2d(smem_u32(Qb(2)), &tm_bw, smem_u32(q_full), 0, brow);
+            }
+        }
+        // K' blocks and V blocks of a stage are separate transactions: K'(t) is reloadable as soon as S'(t-2) has been
+        // computed (a full tile before the PV MMAs of t-2 finish), so the S' MMAs - which run one tile ahead of the PV
+        // MMAs - never wait for the TMA round trip.  Issue order: K'(0) K'(1) V(0) K'(2) V(1) ...
+        PF_DECL
+        if (lane == 0) {
+            for (int i = 0; i <= T; ++i) {
+                if (i < T && (i & 1) == 0) {  // K' of the pair (i, i + 1); a missing second tile loads rows nobody reads
+                    const int pr = i >> 1;
+                    PF(1);
+                    if (pr >= 1) mbar_wait(smem_u32(&k_empty[0]), (pr & 1) ^ 1);
+                    PF(0);
+                    const uint32_t fb = smem_u32(&k_full[0]);
+                    mbar_expect_tx(fb, 2 * nkb * AP_BLK);
+                    for (int u = 0; u < 2; ++u) {
+                        const int key0 = (i + u) * AP_KEYS;
+                        if (MODE == ET_ATTN_DELTA) tma_load_2d(smem_u32(Kb(u, 0)), &tm_kv, fb, h * 64, b * a.k + key0);
+                        else tma_load_2d(smem_u32(Kb(u, 0)), &tm_kv, fb, a.D + h * 64, b * a.N + key0);
+                        if (a.has_bias) {
+                            const int orow = (MODE == ET_ATTN_DELTA) ? b * a.k + key0 : key0;
+                            tma_load_2d(smem_u32(Kb(u, 1)), &tm_oh, fb, 0, orow);
+                            tma_load_2d(smem_u32(Kb(u, 2)), &tm_oh, fb, 64, orow);
+                        }
+                    }
+                }
+                if (i >= 1) {
+                    const int j = i - 1, u = j & 1, key0 = j * AP_KEYS;
+                    PF(1);
+                    if (j >= 2) mbar_wait(smem_u32(&pv_done[u]), ((j >> 1) & 1) ^ 1);  // tile j-2: the PV MMAs are done with slot u
+                    PF(2);
+                    const uint32_t fb = smem_u32(&v_full[u]);
+                    mbar_expect_tx(fb, (MODE == ET_ATTN_DELTA ? 2 : 1) * AP_BLK);
+                    if (MODE == ET_ATTN_DELTA) {
+                        const int r0 = b * a.k + key0;
+                        tma_load_2d(smem_u32(V1(u)), &tm_kv, fb, h * 64, a.sel_rows + r0);
+                        tma_load_2d(smem_u32(V2(u)), &tm_kv, fb, h * 64, 2 * a.sel_rows + r0);
+                    } else {
+                        tma_load_2d(smem_u32(V1(u)), &tm_kv, fb, 2 * a.D + h * 64, b * a.N + key0);
+                    }
+                }
+            }
+        }
+        PF(1);
+        if (lane == 0) PF_FLUSH(0);
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc_ex(128, 2 * AP_KEYS, a.is_bf16, 0);
+            // PV products: A = [key][row] tiles (MN-major), B = V tiles (MN-major); the p . Vd product is subtracted
+            const uint32_t idesc_o = umma_idesc_ex(128, 64, a.is_bf16, 1) | (1u << 15);
+            const uint32_t idesc_neg = idesc_o | (1u << 13);  // a_negate
+            PF_DECL
+            mbar_wait(smem_u32(q_full), 0);
+            PF(7);
+            auto issue_s = [&](int pr) {  // S' of the tile pair pr (128 keys) into pair buffer pr & 1
+                const int w = pr & 1;
+                mbar_wait(smem_u32(&k_full[0]), pr & 1);
+                PF(0);
+                mbar_wait(smem_u32(&s_empty[w]), ((pr >> 1) & 1) ^ 1);
+                PF(1);
+                tcgen05_fence_after();
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint64_t dq = umma_smem_desc(smem_u32(Qb(kb)));
+                    const uint64_t dk = umma_smem_desc(smem_u32(Kb(0, kb)));  // 128 key rows: tiles u = 0, 1 back to back
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tcgen05_mma_f16(tmem_base + w * 2 * AP_KEYS, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s,
+                                        (kb > 0 || kk > 0));
+                }
+                tcgen05_commit(smem_u32(&s_full[w]));
+                tcgen05_commit(smem_u32(&k_empty[0]));
+                PF(2);
+            };
+            auto issue_pv = [&](int t) {
+                const int u = t & 1;
+                mbar_wait(smem_u32(p_ready), t & 1);
+                PF(3);
+                mbar_wait(smem_u32(&v_full[u]), (t >> 1) & 1);
+                PF(8);
+                tcgen05_fence_after();
+                const uint64_t dan = umma_smem_desc_mn_a(smem_u32(An));
+                const uint64_t dv1 = umma_smem_desc_mn(smem_u32(V1(u)));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)  // 16 keys per step = 16 lines of 128 B (2048 B) in the A and V tiles
+                    tcgen05_mma_f16(tmem_o, dan + (uint64_t)(128 * kk), dv1 + (uint64_t)(128 * kk), idesc_o, (t > 0 || kk > 0));
+                PF(4);
+                if (MODE == ET_ATTN_DELTA) {
+                    mbar_wait(smem_u32(&ps_full[t % AP_PT_STAGES]), (t / AP_PT_STAGES) & 1);  // old state tile landed
+                    PF(5);
+                    fence_proxy_async();  // cp.async (generic proxy) writes -> visible to the tensor core
+                    const uint64_t dp = umma_smem_desc_mn_a(smem_u32(Pt(t % AP_PT_STAGES)));
+                    const uint64_t dv2 = umma_smem_desc_mn(smem_u32(V2(u)));
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tcgen05_mma_f16(tmem_o, dp + (uint64_t)(128 * kk), dv2 + (uint64_t)(128 * kk), idesc_neg, 1u);
+                }
+                tcgen05_commit(smem_u32(&pv_done[u]));
+                if (t == T - 1) tcgen05_commit(smem_u32(o_full));
+                PF(6);
+            };
+            // order per pair: PV(2p), S'(p + 1), PV(2p + 1): K'(p + 1) can only be fetched once S'(p) is complete, so S'(p + 1)
+            // goes behind the first PV of the pair (its TMA round trip is hidden) and is still ready before softmax(2p + 2)
+            if (T > 0) issue_s(0);
+            for (int t = 0; t < T; ++t) {
+                issue_pv(t);
+                if ((t & 1) == 0 && t + 2 < T) issue_s((t >> 1) + 1);
+            }
+            PF_FLUSH(1);
+        }
+    } else if (warp < 4) {
+        if (!kWideMovers) state_movers();  // warps 2-3 (spare in the 16-mover build)
+    } else if (warp < 12) {
         // ------------------------------------------------------------------ softmax / epilogue
+        if (kWideMovers) setmaxnreg_inc<104>();
         const int quarter = warp & 3;
         const int half = (warp - 4) >> 2;  // key columns [32 half, +32) of every 64-key tile
         const int row = quarter * 32 + lane;
@@ -586,15 +621,16 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             prev[c] = (MODE == ET_ATTN_DELTA) ? *reinterpret_cast<const uint4*>(acc + off + c * 8) : make_uint4(0, 0, 0, 0);
         PF_DECL
         for (int t = 0; t < T; ++t) {
-            const int u = t & 1;
-            const uint32_t ph = (t >> 1) & 1;
+            const int u = (t >> 1) & 1;                      // pair buffer
+            const uint32_t ph = (t >> 2) & 1;
+            const uint32_t scol = (uint32_t)(u * 2 * AP_KEYS + (t & 1) * AP_KEYS + half * 32);
             PF(11);
             mbar_wait(smem_u32(&s_full[u]), ph);
             PF(0);
             tcgen05_fence_after();
             uint32_t v0[16], v1[16];  // lanes 0-15 / 16-31 of this warp's TMEM quarter
-            tmem_load_16x256b_x4(taddr + (uint32_t)(u * AP_KEYS + half * 32), v0);
-            tmem_load_16x256b_x4(taddr + (16u << 16) + (uint32_t)(u * AP_KEYS + half * 32), v1);
+            tmem_load_16x256b_x4(taddr + scol, v0);
+            tmem_load_16x256b_x4(taddr + (16u << 16) + scol, v1);
             tmem_wait_ld();
             tcgen05_fence_before();
             __syncwarp();
@@ -645,7 +681,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(smem_u32(o_full), 0);
             PF(12);
             tcgen05_fence_after();
-            tmem_load_32x32(taddr + (uint32_t)(2 * AP_KEYS + half * 32), o);
+            tmem_load_32x32(taddr + (uint32_t)(4 * AP_KEYS + half * 32), o);
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = 0u;
@@ -670,12 +706,15 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         PF(14);
         if (lane == 0 && warp == 4) PF_FLUSH(2);
+    } else {
+        if (kWideMovers) setmaxnreg_dec<56>();
+        state_movers();
     }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 

@@ -44,6 +44,7 @@ struct Win2Args {
     const void* rel_x;      // (ww, ww, 64)
     void* out;
     int B, N, gh, gw, wh, ww, nwx, nwy, H, D, Wn, NK, hq, has_bias;
+    int inv_ww;  // (1 << 20) / ww + 1: x / ww == (x * inv_ww) >> 20 for x < 4096, ww <= 16 (no integer division in the kernel)
     float c1;
 };
 
@@ -105,6 +106,7 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwin = a.nwx * a.nwy;
+    auto div_ww = [&](int x) { return (x * a.inv_ww) >> 20; };
     const int half = blockIdx.x & 1, bw = blockIdx.x >> 1, h = blockIdx.y;
     const int b = bw / nwin, win = bw - b * nwin;
     const int wy = win / a.nwx, wx = win - wy * a.nwx;
@@ -177,7 +179,8 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         const int quarter = warp & 3;          // TMEM lane quarter of this warp
         const int ch = (warp - 2) >> 2;        // key-column half (and, for the bias step, y / x part)
         const int row = quarter * 32 + lane;   // query row inside the CTA tile
-        const int ly = y0 + row / a.ww, lx = row % a.ww;  // window-local coordinates of the query
+        const int ry_ = div_ww(row);
+        const int ly = y0 + ry_, lx = row - ry_ * a.ww;  // window-local coordinates of the query
         const uint16_t* pad = static_cast<const uint16_t*>(a.pad_token);
 
         // ---- operands that no TMA writes: the E table (in the V region), the one-hot key block, zero pad rows of V later
@@ -198,16 +201,21 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
                 }
             }
-            // one-hot block: key j -> 1 at column (j / ww) and at column 16 + (j % ww); columns 0..31 = chunks 0..3
-            for (int c = st; c < a.NK * 4; c += 256) {
-                const int j = c >> 2, chunk = c & 3;
-                uint32_t w4[4] = {0, 0, 0, 0};
-                if (j < a.Wn) {
-                    const int hot = chunk < 2 ? j / a.ww : 16 + j % a.ww;
-                    const int d = hot - chunk * 8;
-                    if (d >= 0 && d < 8) w4[d >> 1] = one_elem<BF16>() << ((d & 1) * 16);
+            // one-hot block: key j -> 1 at column (j / ww) and at column 16 + (j % ww); columns 0..31 = chunks 0..3.
+            // One thread per key: chunk c holds columns 8c .. 8c + 7, element e of a chunk sits in word e / 2, half e % 2.
+            if (st < a.NK) {
+                const int j = st;
+                const int ky = div_ww(j), kx = j - ky * a.ww;
+                const uint32_t one = one_elem<BF16>();
+#pragma unroll
+                for (int chunk = 0; chunk < 4; ++chunk) {
+                    const int d = (chunk < 2 ? ky : 16 + kx) - chunk * 8;
+                    const bool on = j < a.Wn && d >= 0 && d < 8;
+                    const uint32_t wv = on ? one << ((d & 1) * 16) : 0u;
+                    const int wi = on ? d >> 1 : -1;
+                    *reinterpret_cast<uint4*>(Koh + j * 128 + ((chunk ^ (j & 7)) << 4)) =
+                        make_uint4(wi == 0 ? wv : 0u, wi == 1 ? wv : 0u, wi == 2 ? wv : 0u, wi == 3 ? wv : 0u);
                 }
-                *reinterpret_cast<uint4*>(Koh + j * 128 + ((chunk ^ (j & 7)) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
         }
         // rows [Wn, NK) of K must be finite?  No: their S' columns are never read.  (V pad rows are zeroed below.)
@@ -217,14 +225,15 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         if (edge) {
             for (int c = st; c < a.Wn * 8; c += 256) {  // keys
                 const int r = c >> 3, chunk = c & 7;
-                const int ky = r / a.ww, kx = r - ky * a.ww;
+                const int ky = div_ww(r), kx = r - ky * a.ww;
                 if (wy * a.wh + ky >= a.gh || wx * a.ww + kx >= a.gw)
                     *reinterpret_cast<uint4*>(Kk + r * 128 + ((chunk ^ (r & 7)) << 4)) =
                         *reinterpret_cast<const uint4*>(pad + a.D + h * 64 + chunk * 8);
             }
             for (int c = st; c < nq * 8; c += 256) {    // queries of this half
                 const int r = c >> 3, chunk = c & 7;
-                const int qy = y0 + r / a.ww, qx = r % a.ww;
+                const int qr = div_ww(r);
+                const int qy = y0 + qr, qx = r - qr * a.ww;
                 if (wy * a.wh + qy >= a.gh || wx * a.ww + qx >= a.gw)
                     *reinterpret_cast<uint4*>(Qq + r * 128 + ((chunk ^ (r & 7)) << 4)) =
                         *reinterpret_cast<const uint4*>(pad + h * 64 + chunk * 8);
@@ -275,14 +284,20 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         tcgen05_fence_after();
         float mx = -1e30f;
         for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-            if (c0 + 32 <= c_hi) {
+            if (c0 + 32 <= min(c_hi, a.Wn)) {  // whole block of real keys: no per-element masks (a warp-uniform branch)
                 uint32_t t[32];
                 tmem_load_32x32(trow + (uint32_t)c0, t);
+                float m4[4] = {mx, -1e30f, -1e30f, -1e30f};
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c0 + i < a.Wn) mx = fmaxf(mx, __uint_as_float(t[i]));
+                for (int i = 0; i < 32; i += 8) {
+                    m4[0] = fmaxf(m4[0], fmaxf(__uint_as_float(t[i]), __uint_as_float(t[i + 1])));
+                    m4[1] = fmaxf(m4[1], fmaxf(__uint_as_float(t[i + 2]), __uint_as_float(t[i + 3])));
+                    m4[2] = fmaxf(m4[2], fmaxf(__uint_as_float(t[i + 4]), __uint_as_float(t[i + 5])));
+                    m4[3] = fmaxf(m4[3], fmaxf(__uint_as_float(t[i + 6]), __uint_as_float(t[i + 7])));
+                }
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             } else {
-                for (int c1 = c0; c1 < c_hi; c1 += 8) {
+                for (int c1 = c0; c1 < min(c0 + 32, c_hi); c1 += 8) {
                     uint32_t t[8];
                     tmem_load_32x8(trow + (uint32_t)c1, t);
 #pragma unroll
@@ -295,31 +310,53 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         pair_sync(1 + quarter);
         mx = fmaxf(mx, xchg[(ch ^ 1) * 128 + row]);
         const float m2 = mx * a.c1;
+        const f32x2 c1c1 = f2_pack(a.c1, a.c1), nm2 = f2_pack(-m2, -m2);
+        f32x2 sum2 = f2_pack(0.f, 0.f);
         float sum = 0.f;
-        auto emit8 = [&](int key0, const uint32_t* t) {  // keys key0 .. key0 + 7 -> one 16-byte chunk of the K-major P row
+        auto p_chunk = [&](int key0) {  // the 16-byte chunk of keys key0 .. key0 + 7 in this row of the K-major P operand
+            const int kc = key0 >> 3;
+            return reinterpret_cast<uint4*>(smem + (kc >> 3) * P_ATOM + row * 128 + (((kc & 7) ^ (row & 7)) << 4));
+        };
+        auto emit8_full = [&](int key0, const uint32_t* t) {  // packed fp32 math: two keys per FFMA2 / FADD2 issue slot
+            uint32_t w4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float x0, x1;
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(t[2 * i]), __uint_as_float(t[2 * i + 1])), c1c1, nm2), x0, x1);
+                const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                sum2 = f2_add(sum2, f2_pack(p0, p1));
+                w4[i] = pack2<BF16>(p0, p1);
+            }
+            *p_chunk(key0) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        };
+        auto emit8 = [&](int key0, const uint32_t* t) {  // masked form for the block that holds the padding keys
             float p[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 p[i] = (key0 + i < a.Wn) ? ex2_approx(fmaf(__uint_as_float(t[i]), a.c1, -m2)) : 0.f;
                 sum += p[i];
             }
-            const int kc = key0 >> 3;
-            *reinterpret_cast<uint4*>(smem + (kc >> 3) * P_ATOM + row * 128 + (((kc & 7) ^ (row & 7)) << 4)) =
-                make_uint4(pack2<BF16>(p[0], p[1]), pack2<BF16>(p[2], p[3]), pack2<BF16>(p[4], p[5]), pack2<BF16>(p[6], p[7]));
+            *p_chunk(key0) = make_uint4(pack2<BF16>(p[0], p[1]), pack2<BF16>(p[2], p[3]), pack2<BF16>(p[4], p[5]), pack2<BF16>(p[6], p[7]));
         };
         for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-            if (c0 + 32 <= c_hi) {
+            if (c0 + 32 <= min(c_hi, a.Wn)) {
                 uint32_t t[32];
                 tmem_load_32x32(trow + (uint32_t)c0, t);
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) emit8(c0 + i, t + i);
+                for (int i = 0; i < 32; i += 8) emit8_full(c0 + i, t + i);
             } else {
-                for (int c1 = c0; c1 < c_hi; c1 += 8) {
+                for (int c1 = c0; c1 < min(c0 + 32, c_hi); c1 += 8) {
                     uint32_t t[8];
                     tmem_load_32x8(trow + (uint32_t)c1, t);
-                    emit8(c1, t);
+                    if (c1 + 8 <= a.Wn) emit8_full(c1, t);
+                    else emit8(c1, t);
                 }
             }
+        }
+        {
+            float s0, s1;
+            f2_unpack(sum2, s0, s1);
+            sum += s0 + s1;
         }
         pair_sync(1 + quarter);  // both maxima have been read
         xchg[ch * 128 + row] = sum;
@@ -330,7 +367,7 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         if (edge) {
             for (int c = st; c < a.Wn * 8; c += 256) {
                 const int r = c >> 3, chunk = c & 7;
-                const int ky = r / a.ww, kx = r - ky * a.ww;
+                const int ky = div_ww(r), kx = r - ky * a.ww;
                 if (wy * a.wh + ky >= a.gh || wx * a.ww + kx >= a.gw)
                     *reinterpret_cast<uint4*>(Vs + r * 128 + ((chunk ^ (r & 7)) << 4)) =
                         *reinterpret_cast<const uint4*>(pad + 2 * a.D + h * 64 + chunk * 8);
@@ -400,6 +437,7 @@ int et_tc_window2_attention(const void* qkv, const void* pad_token, const void* 
     a.pad_token = pad_token; a.rel_y = rel_y; a.rel_x = rel_x; a.out = out; a.B = B; a.N = N; a.gh = gh; a.gw = gw; a.wh = wh; a.ww = ww;
     a.nwy = (gh + wh - 1) / wh; a.nwx = (gw + ww - 1) / ww; a.H = H; a.D = H * 64; a.Wn = wh * ww;
     a.NK = (a.Wn + 15) / 16 * 16; a.hq = (wh + 1) / 2; a.has_bias = rel_y != nullptr ? 1 : 0; a.c1 = 0.125f * kLog2e;
+    a.inv_ww = (1 << 20) / ww + 1;
     const int nwin = a.nwx * a.nwy;
     int rc;
     if ((rc = et_raise_smem(tc_window2_kernel<true>, SMEM_BYTES))) return rc;

@@ -68,6 +68,7 @@ struct GateArgs {
     const void* xa;
     const void* xb;
     void* xsum;
+    void* c_out;  // optional: the gate input c = LN(x) of every token (gather source of et_linear_gather)
     const void* ln_w;
     const void* ln_b;
     float eps;
@@ -393,6 +394,14 @@ __global__ void __launch_bounds__(kGateThreads) gate_select_kernel(const GateArg
             }
         }
         if (ln_w != nullptr) layer_norm_row<T, LPT, CPL>(v, ln_w, ln_b, nchunks, lane, a.D, a.eps);
+        if (a.c_out != nullptr && valid) {
+            T* c_out = static_cast<T*>(a.c_out);
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int ch = lane + c * LPT;
+                if (ch < nchunks) st16(c_out + off + (size_t)ch * VEC, pack16<T>(&v[c * VEC]));
+            }
+        }
         float ss = 0.f;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
@@ -708,14 +717,14 @@ int et_device_info(int device, int* cc_major, int* cc_minor, int* sm_count) {
     return ET_OK;
 }
 
-int et_gate_select(const void* xa, const void* xb, void* xsum_out, const void* ln_w, const void* ln_b, float ln_eps,
+int et_gate_select(const void* xa, const void* xb, void* xsum_out, void* c_out, const void* ln_w, const void* ln_b, float ln_eps,
                    const void* p, int64_t R, int64_t N, int64_t D, int dtype, int mode, int64_t k, float threshold,
                    float* norm_out, int64_t* idx_out, int32_t* count_out, int32_t* ticket, void* stream) {
     ET_CHECK_ARG(xa && norm_out && idx_out && ticket, "et_gate_select: null pointer");
     ET_CHECK_ARG(R > 0 && N > 0 && D > 0 && R <= 65535 && N <= 524280, "et_gate_select: bad shape R=%lld N=%lld D=%lld",
                  (long long)R, (long long)N, (long long)D);
     ET_CHECK_ARG((ln_w == nullptr) == (ln_b == nullptr), "et_gate_select: ln_w / ln_b must both be set or both null");
-    ET_CHECK_ARG(et_aligned16(xa) && et_aligned16(xb) && et_aligned16(xsum_out) && et_aligned16(p) &&
+    ET_CHECK_ARG(et_aligned16(xa) && et_aligned16(xb) && et_aligned16(xsum_out) && et_aligned16(c_out) && et_aligned16(p) &&
                      et_aligned16(ln_w) && et_aligned16(ln_b),
                  "et_gate_select: pointers must be 16-byte aligned");
     if (mode == ET_SELECT_TOPK) {
@@ -726,7 +735,7 @@ int et_gate_select(const void* xa, const void* xb, void* xsum_out, const void* l
         ET_CHECK_ARG(mode == ET_SELECT_THRESHOLD && count_out, "et_gate_select: bad mode / missing count_out");
     }
     GateArgs a;
-    a.xa = xa; a.xb = xb; a.xsum = xsum_out; a.ln_w = ln_w; a.ln_b = ln_b; a.eps = ln_eps; a.p = p;
+    a.xa = xa; a.xb = xb; a.xsum = xsum_out; a.c_out = c_out; a.ln_w = ln_w; a.ln_b = ln_b; a.eps = ln_eps; a.p = p;
     a.N = (int)N; a.D = (int)D; a.mode = mode; a.k = (int)k; a.norm = norm_out;
     a.idx = reinterpret_cast<long long*>(idx_out); a.count = count_out; a.ticket = ticket;
     a.dbg = g_gate_dbg;

@@ -30,14 +30,68 @@ constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 struct LinearArgs {
     const void* bias;
     void* out;
-    const long long* idx;
+    const long long* idx;    // scatter: output row of A row m is (m / k) * n_out_rows + idx[m]
+    const long long* a_idx;  // gather:  A row m is row (m / k) * a_rows + a_idx[m] of the source tensor (TMA tile::gather4)
+    const void* a_src;       // the gather source (R * a_rows, K) and, optionally, the gate state of the same shape that the
+    void* state;             // CTAs of the first column of tiles advance: state[row] = a_src[row] for every gathered row
     const int* count;
     long long ld_out;
-    int M, K, n_feat, act, k, n_out_rows, is_bf16;
+    int M, K, n_feat, act, k, n_out_rows, a_rows, is_bf16;
     unsigned long long* prof;
 };
 
 using namespace et_tc;
+
+// Four rows of a 2-D tensor (tensor map with a one-row box), each 64 elements wide from column c0, land as four consecutive
+// 128-byte rows of the destination in the 128B-swizzled K-major operand layout (profiles/microbench/gather4_probe.cu).
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int r0, int r1, int r2, int r3) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        :
+        : "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+}
+// Source rows of the four A rows m .. m + 3 that lane `lane` of the producer warp gathers (rows past M or past the
+// device-side count repeat a valid row: their results are never stored).
+__device__ __forceinline__ void gather_rows(const LinearArgs& args, int m_first, int (&r)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = min(m_first + i, args.M - 1);
+        const int b = m / args.k, j = m - b * args.k;
+        const bool valid = args.count == nullptr || j < args.count[b];
+        r[i] = b * args.a_rows + (valid ? (int)args.a_idx[m] : 0);
+    }
+}
+
+// Gate-state advance p[idx] = c[idx] (reference modules.py:151) for the 16 tile rows m_first .. m_first + 15, by one warp:
+// plain 16-byte copies of the gathered source rows, issued by epilogue warps while the mainloop runs.
+__device__ __forceinline__ void advance_state_rows(const LinearArgs& args, int m_first, int lane) {
+    const uint4* src = static_cast<const uint4*>(args.a_src);
+    uint4* dst = static_cast<uint4*>(args.state);
+    const int cpr = args.K >> 3;  // 16-byte chunks per row
+#pragma unroll 1
+    for (int r = 0; r < 16; r += 4) {
+        long long row[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m_first + r + i;
+            row[i] = -1;
+            if (m < args.M) {
+                const int b = m / args.k, j = m - b * args.k;
+                if (args.count == nullptr || j < args.count[b]) row[i] = ((long long)b * args.a_rows + args.a_idx[m]) * cpr;
+            }
+        }
+        for (int c = lane; c < cpr; c += 32) {
+            uint4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (row[i] >= 0) v[i] = src[row[i] + c];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (row[i] >= 0) dst[row[i] + c] = v[i];
+        }
+    }
+}
 
 // et_debug_set(7, device pointer to 3 x 16 u64): per-role cycle buckets of linear_tcgen05_kernel, summed over CTAs
 // (profiling build only: make prof).
@@ -142,7 +196,40 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const uint32_t tmem_base = *tmem_slot;
     GPF(0);  // prologue: barrier init, TMEM allocation, CTA sync
 
-    if (warp == 0) {
+    if (warp == 0 && args.a_idx != nullptr) {
+        // ---- gathered A operand: the whole warp produces; lane l fetches rows 4 l .. 4 l + 3 of each 128-row half with one
+        // TMA gather4 per k-block straight from the gate state (the rows selected by the gate index), lane 0 fetches W
+        const int pre = num_k_blocks < STAGES ? num_k_blocks : STAGES;
+        if (lane == 0) {
+            for (int kb = 0; kb < pre; ++kb) {
+                const uint32_t fb = smem_u32(&full_bar[kb]);
+                mbar_expect_tx(fb, L::STAGE_BYTES);
+                tma_load_2d(smem_u32(smem + kb * L::STAGE_BYTES) + L::A_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+            }
+        }
+        et_pdl_wait();
+        int rows[MH][4];
+#pragma unroll
+        for (int hh = 0; hh < MH; ++hh) gather_rows(args, m0 + hh * BLOCK_M + 4 * lane, rows[hh]);
+        __syncwarp();
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t a_dst = smem_u32(smem + s * L::STAGE_BYTES);
+            const uint32_t fb = smem_u32(&full_bar[s]);
+            if (kb >= pre) {
+                mbar_wait(smem_u32(&empty_bar[s]), ((kb / STAGES) & 1) ^ 1);
+                if (lane == 0) {
+                    mbar_expect_tx(fb, L::STAGE_BYTES);
+                    tma_load_2d(a_dst + L::A_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int hh = 0; hh < MH; ++hh)
+                tma_gather4(a_dst + hh * A_TILE_BYTES + lane * 512, &tmap_a, fb, kb * BLOCK_K, rows[hh][0], rows[hh][1], rows[hh][2],
+                            rows[hh][3]);
+        }
+    } else if (warp == 0) {
         if (lane == 0) {
             const int pre = num_k_blocks < STAGES ? num_k_blocks : STAGES;
             for (int kb = 0; kb < pre; ++kb) {  // weights are never written by a kernel: fetch them ahead of the wait
@@ -215,6 +302,10 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                                       : make_uint4(0, 0, 0, 0);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (args.state != nullptr && blockIdx.x == 0) {
+#pragma unroll 1
+            for (int hh = 0; hh < MH; ++hh) advance_state_rows(args, m0 + hh * BLOCK_M + ew * 16, lane);
+        }
 #pragma unroll 1
         for (int hh = 0; hh < MH; ++hh) {
         const int m = m0 + hh * BLOCK_M + row;
@@ -375,7 +466,28 @@ linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 0 && args.a_idx != nullptr) {
+        // gathered A operand (see linear_tcgen05_kernel): the whole warp produces, lane l owns rows 4 l .. 4 l + 3 of the tile
+        et_pdl_wait();
+        int kbg = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            int rows[4];
+            gather_rows(args, m0 + 4 * lane, rows);
+            for (int kb = 0; kb < num_k_blocks; ++kb, ++kbg) {
+                const int s = kbg % STAGES;
+                mbar_wait(smem_u32(&empty_bar[s]), ((kbg / STAGES) & 1) ^ 1);
+                const uint32_t dst = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint32_t fb = smem_u32(&full_bar[s]);
+                if (lane == 0) {
+                    mbar_expect_tx(fb, L::STAGE_BYTES);
+                    tma_load_2d(dst + A_TILE_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+                }
+                __syncwarp();
+                tma_gather4(dst + lane * 512, &tmap_a, fb, kb * BLOCK_K, rows[0], rows[1], rows[2], rows[3]);
+            }
+        }
+    } else if (warp == 0) {
         if (lane == 0) {
             et_pdl_wait();
             GPF_DECL
@@ -467,6 +579,7 @@ linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
                 s_row[row] = valid ? (int)out_row : -1;
             }
+            if (args.state != nullptr && n0 == 0) advance_state_rows(args, m0 + ew * 16, lane);
             __syncwarp();
             GPF(4);
             mbar_wait(smem_u32(&tmem_full[buf]), (it >> 1) & 1);
@@ -564,7 +677,8 @@ int launch_linear(const void* A, const void* W, const LinearArgs& args, cudaStre
     int rc = et_raise_smem(linear_tcgen05_kernel<BLOCK_N, STAGES, MH>, L::TOTAL);
     if (rc) return rc;
     CUtensorMap ta, tw;
-    rc = make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M * MH, args.is_bf16);
+    rc = args.a_idx ? make_tmap_2d(&ta, A, (long long)(args.M / args.k) * args.a_rows, args.K, 1, args.is_bf16)  // one-row box: gather4
+                    : make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M * MH, args.is_bf16);
     if (rc) return rc;
     rc = make_tmap_2d(&tw, W, args.n_feat, args.K, BLOCK_N, args.is_bf16);
     if (rc) return rc;
@@ -581,7 +695,8 @@ int launch_persistent(const void* A, const void* W, const LinearArgs& args, cuda
     if (rc) return rc;
     const int sms = et_sm_count();
     CUtensorMap ta, tw;
-    rc = make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M, args.is_bf16);
+    rc = args.a_idx ? make_tmap_2d(&ta, A, (long long)(args.M / args.k) * args.a_rows, args.K, 1, args.is_bf16)
+                    : make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M, args.is_bf16);
     if (rc) return rc;
     rc = make_tmap_2d(&tw, W, args.n_feat, args.K, BLOCK_N, args.is_bf16);
     if (rc) return rc;
@@ -661,11 +776,14 @@ int et_debug_set(int key, long long value) {
     return et_fail(ET_ERR_ARG, "et_debug_set: unknown key %d", key);
 }
 
-int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bias, int64_t n_feat, int act, void* out,
-              int64_t ld_out, const int64_t* idx, const int32_t* count, int64_t k, int64_t n_out_rows, int dtype,
-              void* stream) {
+// Shared body of et_linear / et_linear_gather.  a_idx != nullptr: A is the gather source (M / k * a_rows, K) and the A operand
+// rows are A[(m / k) * a_rows + a_idx[m]] (TMA gather4 producer); `state` (same shape as the source) is advanced at those rows.
+static int linear_impl(const void* A, const int64_t* a_idx, int64_t a_rows, void* state, int64_t M, int64_t K, const void* W,
+                       const void* bias, int64_t n_feat, int act, void* out, int64_t ld_out, const int64_t* idx,
+                       const int32_t* count, int64_t k, int64_t n_out_rows, int dtype, void* stream) {
     ET_CHECK_ARG(A && W && out, "et_linear: null pointer");
     if (dtype == ET_F32) {  // fp32 models: CUDA-core SGEMM with the same epilogue (et_generic.cu)
+        if (a_idx != nullptr) return et_fail(ET_ERR_UNSUPPORTED, "et_linear_gather: 16-bit dtypes only (fp32 models gather with et_gate_gather)");
         ET_CHECK_ARG(M >= 0 && K > 0 && n_feat > 0 && M < (1LL << 31), "et_linear: bad shape");
         ET_CHECK_ARG(et_aligned16(A) && et_aligned16(W), "et_linear: pointers must be 16-byte aligned");
         ET_CHECK_ARG(act == ET_ACT_NONE || act == ET_ACT_GELU, "et_linear: unknown activation %d", act);
@@ -685,11 +803,15 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
                  "et_linear: pointers must be 16-byte aligned");
     ET_CHECK_ARG(act == ET_ACT_NONE || act == ET_ACT_GELU, "et_linear: unknown activation %d", act);
     if (idx != nullptr) ET_CHECK_ARG(k > 0 && M % k == 0 && n_out_rows > 0, "et_linear: scatter needs k | M and n_out_rows");
-    ET_CHECK_ARG(count == nullptr || idx != nullptr, "et_linear: count needs idx");
+    if (a_idx != nullptr)
+        ET_CHECK_ARG(k > 0 && M % k == 0 && a_rows > 0 && (M / k) * a_rows < (1LL << 31) && et_aligned16(state),
+                     "et_linear_gather: gather needs k | M, a_rows and a source of fewer than 2^31 rows");
+    ET_CHECK_ARG(count == nullptr || idx != nullptr || a_idx != nullptr, "et_linear: count needs idx");
     if (M == 0) return ET_OK;
     LinearArgs a;
     a.bias = bias; a.out = out; a.idx = reinterpret_cast<const long long*>(idx); a.count = count; a.ld_out = ld_out;
-    a.M = (int)M; a.K = (int)K; a.n_feat = (int)n_feat; a.act = act; a.k = (int)(idx ? k : 1);
+    a.a_idx = reinterpret_cast<const long long*>(a_idx); a.a_rows = (int)a_rows; a.a_src = A; a.state = state;
+    a.M = (int)M; a.K = (int)K; a.n_feat = (int)n_feat; a.act = act; a.k = (int)((idx || a_idx) ? k : 1);
     a.n_out_rows = (int)n_out_rows; a.is_bf16 = dtype == ET_BF16;
     a.prof = g_gemm_prof;
 
@@ -757,6 +879,20 @@ int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bi
     if (rc) return rc;
     ET_CHECK_LAUNCH("et_linear");
     return ET_OK;
+}
+
+int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bias, int64_t n_feat, int act, void* out,
+              int64_t ld_out, const int64_t* idx, const int32_t* count, int64_t k, int64_t n_out_rows, int dtype,
+              void* stream) {
+    return linear_impl(A, nullptr, 0, nullptr, M, K, W, bias, n_feat, act, out, ld_out, idx, count, k, n_out_rows, dtype, stream);
+}
+
+int et_linear_gather(const void* a_src, int64_t a_rows, const int64_t* a_idx, void* state, int64_t M, int64_t K, const void* W,
+                     const void* bias, int64_t n_feat, int act, void* out, int64_t ld_out, const int64_t* idx,
+                     const int32_t* count, int64_t k, int64_t n_out_rows, int dtype, void* stream) {
+    ET_CHECK_ARG(a_src && a_idx, "et_linear_gather: null pointer");
+    return linear_impl(a_src, a_idx, a_rows, state, M, K, W, bias, n_feat, act, out, ld_out, idx, count, k, n_out_rows, dtype,
+                       stream);
 }
 
 }  // extern "C"

@@ -29,7 +29,7 @@ _SIGNATURES = {
     "et_launch_count": (c_longlong, []),
     "et_last_error": (ctypes.c_char_p, []),
     "et_device_info": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
-    "et_gate_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64,
+    "et_gate_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64,
                                c_int64, c_int64, c_int, c_int, c_int64, c_float, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
     "et_gate_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p,
@@ -44,6 +44,8 @@ _SIGNATURES = {
     "et_debug_elapsed_ms": (c_float, []),
     "et_linear": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64,
                           c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "et_linear_gather": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int,
+                                 c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "et_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                     c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "et_attn_workspace_bytes": (c_int64, [c_int64] * 9 + [c_int]),
@@ -155,7 +157,7 @@ def _ticket(device, rows):
 # op wrappers (torch tensors in, torch tensors out)
 # ----------------------------------------------------------------------------
 def gate_select(xa, p=None, xb=None, want_sum=False, ln=None, eps=1e-6, k=None, threshold=None, ticket=None,
-                device_count=False):
+                device_count=False, c_out=None):
     """
     Fused [add] -> [LayerNorm] -> delta norm -> selection.  xa: (..., N, D).
     Returns (index (..., k) int64, xsum or None).  With `threshold` the result is
@@ -163,6 +165,8 @@ def gate_select(xa, p=None, xb=None, want_sum=False, ln=None, eps=1e-6, k=None, 
     reference's nonzero() does (policies.py:27-28) -- or, with device_count=True,
     (index padded to (..., N), xsum, count (rows,) int32 on the device) with no host
     synchronisation at all (CUDA-graph capturable; consumers take the count pointer).
+    `c_out` (same shape as xa): receives the gate input c = LN(x) of every token, the gather source of
+    linear_gather().
     """
     require_device(xa)
     _dense(xa, "gate input")
@@ -185,13 +189,13 @@ def gate_select(xa, p=None, xb=None, want_sum=False, ln=None, eps=1e-6, k=None, 
         idx = torch.empty(lead + (n,), dtype=torch.int64, device=xa.device)
         count = torch.empty((rows,), dtype=torch.int32, device=xa.device)
         mode, kk, thr = SELECT_THRESHOLD, 0, float(threshold)
-    for t, name in ((p, "gate state"), (xb, "residual")):
+    for t, name in ((p, "gate state"), (xb, "residual"), (c_out, "gate input copy")):
         if t is not None:
             _dense(t, name)
             if t.shape != xa.shape or t.dtype != xa.dtype:
                 raise ValueError(f"eventful_b200: {name} shape/dtype mismatch")
     ln_w, ln_b = (None, None) if ln is None else ln
-    _check(lib().et_gate_select(_p(xa), _p(xb), _p(xsum), _p(ln_w), _p(ln_b), float(eps), _p(p), rows, n, d,
+    _check(lib().et_gate_select(_p(xa), _p(xb), _p(xsum), _p(c_out), _p(ln_w), _p(ln_b), float(eps), _p(p), rows, n, d,
                                 dtype_code(xa), mode, kk, thr, _p(norm), _p(idx), _p(count), _p(ticket), _stream()),
            "et_gate_select")
     if threshold is not None:
@@ -298,6 +302,46 @@ def linear(x, weight, bias, act=ACT_NONE, out=None, idx=None, n_out_rows=0, coun
         raise TypeError(f"eventful_b200.linear: input is {x.dtype}, weight {weight.dtype}; cast the model or the input")
     _check(lib().et_linear(_p(x), m, k_dim, _p(weight), _p(bias), f, int(act), _p(out), out.shape[-1], _p(idx),
                            _p(count), kk, rows_out, dtype_code(x), _stream()), "et_linear")
+    return out
+
+
+def linear_gather(src, a_idx, weight, bias, state=None, act=ACT_NONE, out=None, idx=None, count=None):
+    """
+    y = act(src[b, a_idx[b, j]] @ W^T + b) with the gather done by the GEMM's TMA producer (tile::gather4) and, with
+    `state` (same shape as src), state[b, a_idx[b, j]] = src[b, a_idx[b, j]] advanced by the same kernel.
+    src: (B, N, K), a_idx: (B, k).  `idx` / `out` as in linear() (TokenBuffer scatter); without them y is (B, k, F).
+    """
+    require_device(src)
+    _dense(src, "gather source"), _dense(weight, "weight"), _dense(a_idx, "gather index")
+    if src.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError("eventful_b200.linear_gather: 16-bit dtypes only")
+    n, k_dim = src.shape[-2], src.shape[-1]
+    kk = a_idx.shape[-1]
+    lead = tuple(src.shape[:-2])
+    if tuple(a_idx.shape[:-1]) != lead:
+        raise ValueError("eventful_b200: index leading dims must match the source's")
+    f = weight.shape[0]
+    m = a_idx.numel()
+    if state is not None:
+        _dense(state, "gate state")
+        if state.shape != src.shape or state.dtype != src.dtype:
+            raise ValueError("eventful_b200: gate state shape/dtype mismatch")
+    if idx is None:
+        if out is None:
+            out = torch.empty(lead + (kk, f), dtype=src.dtype, device=src.device)
+        rows_out = 0
+    else:
+        _dense(idx, "index"), _dense(out, "buffer")
+        if idx.shape != a_idx.shape:
+            raise ValueError("eventful_b200: scatter and gather index shapes differ")
+        rows_out = out.shape[-2]
+    if kk == 0:
+        return out
+    if weight.dtype != src.dtype or (bias is not None and bias.dtype != src.dtype):
+        raise TypeError(f"eventful_b200.linear_gather: input is {src.dtype}, weight {weight.dtype}")
+    _check(lib().et_linear_gather(_p(src), n, _p(a_idx), _p(state), m, k_dim, _p(weight), _p(bias), f, int(act), _p(out),
+                                  out.shape[-1], _p(idx), _p(count), kk, rows_out, dtype_code(src), _stream()),
+           "et_linear_gather")
     return out
 
 

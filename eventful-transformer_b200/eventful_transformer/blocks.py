@@ -7,6 +7,8 @@ How a gated block runs here (incremental frame), per gate site:
     et_gate_select   [residual add] + LayerNorm + (c - p) + token norm + radix top-k, one launch
     et_gate_gather   c~ = LN(x)[idx], p[idx] = c~
     et_linear        tcgen05 GEMM on the k gathered rows, rows scattered into the TokenBuffer
+  (opt-in two-launch form, EVENTFUL_B200_FUSE_GATHER=1: et_gate_select also emits c for every token and
+   et_linear_gather gathers c[idx] with TMA tile::gather4, advances p[idx] and scatters -- slower on B200, see FUSE_GATHER)
 and for attention
     et_window_attention   windowed blocks (dense, blocks.py:205-240 of the reference)
     et_global_attention   global blocks: softmax statistics + A-gate / v-gate / delta accumulation
@@ -23,6 +25,7 @@ the model dtype and fp32 models run on the general-precision kernels (csrc/et_ge
 Not implemented: adaptive token sampling (ats_fraction), drop-path in training mode.
 """
 
+import os
 from math import prod, sqrt
 
 import torch
@@ -43,6 +46,22 @@ from eventful_transformer.modules import (
 from eventful_transformer.utils import DropPath, RelativePositionEmbedding
 
 LN_EPS = 1e-6
+
+# Gate sites run et_gate_select -> et_gate_gather -> et_linear.  EVENTFUL_B200_FUSE_GATHER=1 switches to the two-launch form
+# et_gate_select (+ c for every token) -> et_linear_gather (TMA gather4 A operand + state advance in the GEMM).  It is
+# parity-tested but OFF by default: measured on B200 (profiles/r2_gather_gemm_bench.txt) a gather4 moves 512 bytes per TMA
+# instruction against 16 KB for a tile load, and the GEMMs of the gate sites run 1.6-2.2x slower (8 streams: 535 vs 622
+# frames/s end to end), far more than the deleted gather launch saves.
+FUSE_GATHER = os.environ.get("EVENTFUL_B200_FUSE_GATHER", "0") == "1"
+
+
+class _Gathered:
+    """A gate site's selected rows left in place: (source of every token's gate input, index, gate state to advance)."""
+
+    __slots__ = ("src", "index", "state")
+
+    def __init__(self, src, index, state):
+        self.src, self.index, self.state = src, index, state
 
 # single-pass attention kernel is used for dense attention over at most this many keys
 _SMALL_ATTENTION = 512
@@ -206,8 +225,15 @@ class Block(ExtendedModule):
                 self.relative_position.count_fused(b * self.heads, n, n_keys)
         return out
 
+    @staticmethod
+    def _linear(layer, c, **kw):
+        """layer(c) for a materialised c~ or for rows still to be gathered by the GEMM (_Gathered)."""
+        if isinstance(c, _Gathered):
+            return layer.forward_gathered(c.src, c.index, state=c.state, **kw)
+        return layer(c, **kw)
+
     def _mlp(self, c, out=None, idx=None, count=None, rows=None):
-        h = self.mlp_1(c, act=native.ACT_GELU, rows=rows)
+        h = self._linear(self.mlp_1, c, act=native.ACT_GELU, rows=rows, count=count if isinstance(c, _Gathered) else None)
         return self.mlp_2(h, out=out, idx=idx, count=count, rows=rows)
 
     # Pair protocol: input is xa (+ xb), output is (branch, skip) whose sum is the block output.
@@ -244,6 +270,8 @@ class EventfulTokenwiseBlock(Block):
         One gate site on an incremental frame.  Returns (x, c_tilde, index, count) where x = xa (+ xb) is the
         site input (materialised only when there is a residual to add) and count is None (all entries of index
         valid) or a device-side int32 tensor (threshold policy: index is padded to N, no host synchronisation).
+        c_tilde is the gathered tensor, or a _Gathered record when the following linear layer gathers the rows
+        itself and advances gate.p in the same kernel (16-bit models, built-in policies, LayerNorm before the gate).
         """
         ln_p = None if ln is None else self._ln_params(ln)
         pre, post = (None, ln_p) if self.gate_before_ln else (ln_p, None)
@@ -251,13 +279,17 @@ class EventfulTokenwiseBlock(Block):
             gate.counts["gate_flops"] += gate.p.numel()
         spec = _policy_spec(gate.policy, xa.shape[-2])
         count = None
+        fuse = (FUSE_GATHER and spec is not None and post is None and not self.stgt and xa.dtype != torch.float32
+                and xa.shape[-1] % 8 == 0 and gate.p.is_contiguous())
+        c_all = torch.empty_like(xa) if (fuse and pre is not None) else None
         if spec is not None:
             if "threshold" in spec:
                 assert xa.shape[0] == 1  # policies.py:25
                 index, xsum, count = native.gate_select(xa, p=gate.p, xb=xb, want_sum=True, ln=pre, eps=LN_EPS,
-                                                        device_count=True, **spec)
+                                                        device_count=True, c_out=c_all, **spec)
             else:
-                index, xsum = native.gate_select(xa, p=gate.p, xb=xb, want_sum=True, ln=pre, eps=LN_EPS, **spec)
+                index, xsum = native.gate_select(xa, p=gate.p, xb=xb, want_sum=True, ln=pre, eps=LN_EPS, c_out=c_all,
+                                                 **spec)
             x = xsum if xb is not None else xa
         else:  # user-defined policy: materialise the error tensor and call it
             x = native.add(xa, xb) if xb is not None else xa
@@ -265,6 +297,8 @@ class EventfulTokenwiseBlock(Block):
             index = gate.policy(native.sub(c, gate.p), dim=-1)
         index = index.contiguous()
         gate._last_sel = (index, count)  # selection trace (gate.last_index); references, no copy
+        if fuse and index.shape[-1] > 0:
+            return x, _Gathered(x if c_all is None else c_all, index, gate.p), index, count
         if post is not None:
             c_tilde, _ = native.gate_gather(x, index, p=gate.p, ln=post, eps=LN_EPS, ln_after=True,
                                             full_replace=self.stgt, count=count)
@@ -314,12 +348,13 @@ class EventfulTokenwiseBlock(Block):
         n = xa.shape[-2]
         # gate-accumulator 1: LN -> gate -> QKV -> buffer
         x, c1, index, count = self._gate_site(self.qkv_gate, xa, xb, self.input_layer_norm)
-        qkv = self.qkv(c1, out=self.qkv_accumulator.b, idx=index, count=count, rows=self._rows_selected(index, count))
+        qkv = self._linear(self.qkv, c1, out=self.qkv_accumulator.b, idx=index, count=count,
+                           rows=self._rows_selected(index, count))
         attn = self._attention_incremental(qkv, index, count)
         # gate-accumulator 2: gate -> projection -> buffer
         _, c2, index2, count2 = self._gate_site(self.projection_gate, attn, None, None)
-        proj = self.projection(c2, out=self.projection_accumulator.b, idx=index2, count=count2,
-                               rows=self._rows_selected(index2, count2))
+        proj = self._linear(self.projection, c2, out=self.projection_accumulator.b, idx=index2, count=count2,
+                            rows=self._rows_selected(index2, count2))
         # gate-accumulator 3: (+ skip) -> LN -> gate -> MLP -> buffer
         x2, c3, index3, count3 = self._gate_site(self.mlp_gate, proj, x, self.mlp_layer_norm)
         branch = self._mlp(c3, out=self.mlp_accumulator.b, idx=index3, count=count3, rows=self._rows_selected(index3, count3))

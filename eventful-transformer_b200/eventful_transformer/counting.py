@@ -135,6 +135,13 @@ class CountedLinear(_Counted):
         self.count_linear(x.numel() // self.in_features if rows is None else rows)
         return y
 
+    def forward_gathered(self, src, a_idx, state=None, act=native.ACT_NONE, out=None, idx=None, count=None, rows=None):
+        """forward() on the rows src[b, a_idx[b, j]], gathered by the GEMM itself; `state` is advanced at those rows."""
+        y = native.linear_gather(src, a_idx, self.weight.detach(), self.bias.detach(), state=state, act=act, out=out,
+                                 idx=idx, count=count)
+        self.count_linear(a_idx.numel() if rows is None else rows)
+        return y
+
     def forward_linear(self, x):
         """The product alone (reference counting.py:157-158)."""
         self.count_linear(x.numel() // self.in_features, with_bias=False)

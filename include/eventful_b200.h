@@ -53,13 +53,15 @@ int         et_device_info(int device, int* cc_major, int* cc_minor, int* sm_cou
  *   xa       (R, N, D)            gate input (or first addend)
  *   xb       (R, N, D) or NULL    second addend (residual); sum rounded to dtype
  *   xsum_out (R, N, D) or NULL    receives xa + xb
+ *   c_out    (R, N, D) or NULL    receives the gate input c = LayerNorm(x) of every token: the gather source of
+ *                                 et_linear_gather (no separate gather launch between the gate and its linear layer)
  *   ln_w/b   (D) or NULL          LayerNorm affine, eps = ln_eps
  *   p        (R, N, D) or NULL    gate reference state (NULL: the norm of c itself)
  *   norm_out (R, N) float         per-token norms (value already rounded to dtype)
  *   idx_out  (R, k) / (R, N)      selected indices; threshold mode writes count_out[r] of them
  *   ticket   (R) int32            zero-initialised once; self-resetting
  */
-int et_gate_select(const void* xa, const void* xb, void* xsum_out, const void* ln_w, const void* ln_b,
+int et_gate_select(const void* xa, const void* xb, void* xsum_out, void* c_out, const void* ln_w, const void* ln_b,
                    float ln_eps, const void* p, int64_t R, int64_t N, int64_t D, int dtype, int mode,
                    int64_t k, float threshold, float* norm_out, int64_t* idx_out, int32_t* count_out,
                    int32_t* ticket, void* stream);
@@ -122,6 +124,21 @@ float et_debug_elapsed_ms(void);
 int et_linear(const void* A, int64_t M, int64_t K, const void* W, const void* bias, int64_t n_feat, int act,
               void* out, int64_t ld_out, const int64_t* idx, const int32_t* count, int64_t k,
               int64_t n_out_rows, int dtype, void* stream);
+
+/*
+ * The same linear layer with the gate's gather AND its state advance fused in (16-bit dtypes):
+ *     A[m, :] = a_src[(m / k) * a_rows + a_idx[m], :]       A-operand rows fetched by TMA tile::gather4 straight into the
+ *                                                            128B-swizzled tcgen05 operand tiles (no c~ tensor in HBM)
+ *     state[(m / k) * a_rows + a_idx[m], :] = A[m, :]        (state != NULL) the gate reference advances in the same kernel
+ * Replaces: `c.gather(index)` + `self.p.scatter_(index, c~)` of TokenGate.forward_incremental (modules.py:150-151) followed
+ *   by CountedLinear.forward (counting.py:157-162) and TokenBuffer.scatter_ (modules.py:96) -- one launch per gate site.
+ *   a_src (M / k * a_rows, K): the gate input of every token (c_out of et_gate_select, or the un-normalised input);
+ *   a_idx (M) int64: the gate index; state: same shape as a_src or NULL; the other arguments as et_linear
+ *   (idx may be NULL: mlp_1 gathers but does not scatter).  count applies to both the gather and the scatter.
+ */
+int et_linear_gather(const void* a_src, int64_t a_rows, const int64_t* a_idx, void* state, int64_t M, int64_t K,
+                     const void* W, const void* bias, int64_t n_feat, int act, void* out, int64_t ld_out,
+                     const int64_t* idx, const int32_t* count, int64_t k, int64_t n_out_rows, int dtype, void* stream);
 
 /*
  * Dense windowed self-attention of EventfulTokenwiseBlock / Block, fused

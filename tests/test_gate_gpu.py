@@ -85,8 +85,11 @@ def test_fused_add_layernorm_select_and_gather(dtype):
     c = F.layer_norm(x, (d,), w, bias, 1e-6)
     p = (c.float() + 0.3 * torch.randn(b, n, d, generator=g).to(DEV) * (torch.rand(b, n, 1, generator=g).to(DEV) < 0.5)).to(dtype)
     p0 = p.clone()
-    idx, xsum = native.gate_select(xa, p=p, xb=xb, want_sum=True, ln=(w, bias), eps=1e-6, k=k)
+    c_all = torch.empty_like(xa)
+    idx, xsum = native.gate_select(xa, p=p, xb=xb, want_sum=True, ln=(w, bias), eps=1e-6, k=k, c_out=c_all)
     assert torch.equal(xsum, x)
+    idx_plain, _ = native.gate_select(xa, p=p, xb=xb, want_sum=True, ln=(w, bias), eps=1e-6, k=k)
+    assert torch.equal(idx, idx_plain)  # emitting c does not change the selection
     norm = torch.linalg.vector_norm(c - p, dim=-1).float()
     for r in range(b):
         a, ref = set(idx[r].tolist()), set(norm[r].topk(k)[1].tolist())
@@ -98,6 +101,9 @@ def test_fused_add_layernorm_select_and_gather(dtype):
     want_c = c.gather(1, idx.unsqueeze(-1).expand(-1, -1, d))
     tol = dict(rtol=2e-2, atol=2e-2) if dtype != torch.float32 else dict(rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(c_t, want_c, **tol)
+    # the gate input emitted for every token (gather source of et_linear_gather) holds exactly the rows et_gate_gather makes
+    assert torch.equal(c_all.gather(1, idx.unsqueeze(-1).expand(-1, -1, d)), c_t)
+    torch.testing.assert_close(c_all, c, **tol)
     # state advanced exactly at the selected rows, untouched elsewhere; e~ = c~ - p_old exactly (in dtype)
     assert torch.equal(p.gather(1, idx.unsqueeze(-1).expand(-1, -1, d)), c_t)
     mask = torch.ones(b, n, dtype=torch.bool, device=DEV)

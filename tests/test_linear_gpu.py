@@ -186,3 +186,89 @@ def test_device_side_count_skips_whole_tiles_on_the_tensor_core_path():
         want = torch.zeros_like(full)
         want[0, idx[0, :valid]] = full[0, idx[0, :valid]]
         assert torch.equal(got, want), valid
+
+
+def _gather_case(batch, n, k_sel, kdim, f, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randn(batch, n, kdim, generator=g).to(dtype).to(DEV)
+    w = (torch.randn(f, kdim, generator=g) / kdim ** 0.5).to(dtype).to(DEV)
+    b = torch.randn(f, generator=g).to(dtype).to(DEV)
+    idx = torch.stack([torch.randperm(n, generator=g)[:k_sel] for _ in range(batch)]).to(DEV)
+    return src, w, b, idx
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("batch,n,k_sel,kdim,f", [
+    (1, 4096, 2048, 768, 2304), (1, 4096, 2048, 768, 768), (1, 4096, 2048, 768, 3072),  # ViTDet-B gate sites, one stream
+    (8, 4096, 2048, 768, 2304), (8, 4096, 2048, 768, 768),                              # 8 streams: persistent kernel
+    (3, 197, 64, 768, 2304), (2, 300, 131, 72, 136), (1, 50, 1, 64, 8), (2, 64, 64, 40, 264),  # ragged tails, k = N
+])
+def test_linear_gather_equals_linear_on_gathered_rows(batch, n, k_sel, kdim, f, dtype):
+    """et_linear_gather (TMA gather4 A operand + gate-state advance + scatter epilogue) is bit-identical to et_linear on the
+    rows gathered beforehand (same tiles, same arithmetic), advances exactly the selected state rows and leaves the rest."""
+    src, w, b, idx = _gather_case(batch, n, k_sel, kdim, f, dtype, seed=k_sel + f)
+    rows = torch.gather(src, 1, idx[..., None].expand(-1, -1, kdim)).contiguous()
+    for act in (0, 1):
+        state = torch.full_like(src, 3.0)
+        buf = torch.full((batch, n, f), 7.0, dtype=dtype, device=DEV)
+        native.linear_gather(src, idx, w, b, state=state, act=act, out=buf, idx=idx)
+        want = torch.full((batch, n, f), 7.0, dtype=dtype, device=DEV)
+        native.linear(rows, w, b, act=act, out=want, idx=idx)
+        assert torch.equal(buf, want)
+        check(torch.gather(buf, 1, idx[..., None].expand(-1, -1, f)).reshape(-1, f),
+              reference(rows.reshape(-1, kdim), w, b, act), dtype)
+        want_state = torch.full_like(src, 3.0)
+        want_state.scatter_(1, idx[..., None].expand(-1, -1, kdim), rows)
+        assert torch.equal(state, want_state)
+        # no scatter (mlp_1): dense (B, k, F) output, no state
+        y = native.linear_gather(src, idx, w, b, act=act)
+        assert torch.equal(y, native.linear(rows, w, b, act=act))
+
+
+@pytest.mark.parametrize("block_n,persist,mh", [(64, 2, 1), (96, 2, 1), (128, 1, 1), (192, 1, 1), (256, 1, 1), (256, 2, 2), (192, 2, 2)])
+def test_linear_gather_every_kernel_variant(block_n, persist, mh):
+    dtype = torch.bfloat16
+    lib = native.lib()
+    try:
+        lib.et_debug_set(1, block_n), lib.et_debug_set(9, persist), lib.et_debug_set(8, mh if persist == 2 else 0)
+        for batch, n, k_sel, kdim, f in [(2, 1024, 600, 768, 768), (1, 300, 257, 72, 136), (4, 4096, 2048, 3072, 768)]:
+            src, w, b, idx = _gather_case(batch, n, k_sel, kdim, f, dtype, seed=block_n + n)
+            rows = torch.gather(src, 1, idx[..., None].expand(-1, -1, kdim)).contiguous()
+            state = torch.zeros_like(src)
+            buf = torch.zeros((batch, n, f), dtype=dtype, device=DEV)
+            for _ in range(2):
+                native.linear_gather(src, idx, w, b, state=state, out=buf, idx=idx)
+            want = torch.zeros((batch, n, f), dtype=dtype, device=DEV)
+            native.linear(rows, w, b, out=want, idx=idx)
+            assert torch.equal(buf, want)
+            assert torch.equal(state, torch.zeros_like(src).scatter_(1, idx[..., None].expand(-1, -1, kdim), rows))
+    finally:
+        lib.et_debug_set(1, 0), lib.et_debug_set(9, 0), lib.et_debug_set(8, 0)
+
+
+def test_linear_gather_device_side_count():
+    """Threshold policy: only the first count[b] entries of the padded index are gathered, advanced and scattered."""
+    dtype, n, kdim, f = torch.bfloat16, 1024, 768, 2304
+    src, w, b, idx = _gather_case(1, n, n, kdim, f, dtype, seed=3)
+    for found in (0, 1, 127, 128, 700, 1024):
+        count = torch.tensor([found], dtype=torch.int32, device=DEV)
+        state = torch.full_like(src, 3.0)
+        buf = torch.full((1, n, f), 7.0, dtype=dtype, device=DEV)
+        native.linear_gather(src, idx, w, b, state=state, out=buf, idx=idx, count=count)
+        sel = idx[:, :found]
+        rows = torch.gather(src, 1, sel[..., None].expand(-1, -1, kdim)).contiguous()
+        want = torch.full((1, n, f), 7.0, dtype=dtype, device=DEV)
+        if found:
+            native.linear(rows, w, b, out=want, idx=sel.contiguous())
+        assert torch.equal(buf, want), found
+        assert torch.equal(state, torch.full_like(src, 3.0).scatter_(1, sel[..., None].expand(-1, -1, kdim), rows)), found
+
+
+def test_linear_gather_rejects_fp32_and_bad_shapes():
+    src = torch.zeros(1, 16, 64, device=DEV)
+    idx = torch.zeros(1, 4, dtype=torch.int64, device=DEV)
+    with pytest.raises(TypeError):
+        native.linear_gather(src, idx, torch.zeros(8, 64, device=DEV), None)
+    src = src.bfloat16()
+    with pytest.raises(ValueError):
+        native.linear_gather(src, idx, torch.zeros(8, 64, device=DEV, dtype=torch.bfloat16), None, state=torch.zeros(1, 8, 64, device=DEV, dtype=torch.bfloat16))
