@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(kAttnThreads) relpos_bias_kernel(const AttnArg
     constexpr int LD = DH + 8;
     __shared__ __align__(16) T Qs[BQ * LD];
     __shared__ __align__(16) T Ts[BKV * LD];
+    __shared__ __align__(16) T Cs[BQ * LD];  // output tile staging (16-bit dtypes)
     const TokenMap map = make_map(a);
     const int line = blockIdx.x, h = blockIdx.y, bw = blockIdx.z;
     const int nwin = a.windowed ? a.nwx * a.nwy : 1;
@@ -238,18 +239,50 @@ __global__ void __launch_bounds__(kAttnThreads) relpos_bias_kernel(const AttnArg
             load_q_frags<T, DH, LD>(qf, Qs, warp, lane);
             float s[8][4];
             qk_tile<T, DH, LD>(s, qf, Ts, lane);
+            // ld_pad: tensor-core layouts with padded rows. combined: one array [bias_h | bias_w | 0] per token
+            // (pre-zeroed by the caller, bias_w == bias_h); otherwise the pad columns are zero-filled here.
+            const int ld = ld_pad > 0 ? ld_pad : nout;
+            const int rows = rows_pad > 0 ? rows_pad : a.Wn;
+            const int coff = (combined && !ymode) ? lh : 0;
+            const int limit = combined ? nout : ld;
+            if constexpr (sizeof(T) == 2) {
+                if (((ld | coff) & 7) == 0) {
+                    // 16-bit tables with 16-byte aligned rows: the 64 x 64 tile is staged in shared memory and written as
+                    // 16-byte chunks (a token's 64 coordinates are one 128-byte row) instead of one 2-byte store per element
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 4; i += 2) {
+                            const int r = warp * 16 + g + (i >> 1) * 8;
+                            const int c = nt * 8 + tq * 2;
+                            const float v0 = out0 + c < nout ? s[nt][i] * scale : 0.f;
+                            const float v1 = out0 + c + 1 < nout ? s[nt][i + 1] * scale : 0.f;
+                            *reinterpret_cast<uint32_t*>(Cs + r * LD + c) = pack2_rn<T>(v0, v1);
+                        }
+                    __syncthreads();
+                    for (int ch = threadIdx.x; ch < BQ * (BKV / 8); ch += kAttnThreads) {
+                        const int r = ch >> 3, c8 = (ch & 7) * 8;
+                        const int j = tok0 + r, kc0 = out0 + c8;
+                        if (j < ntok && kc0 < limit) {
+                            const int t = ymode ? fixed * lw + j : j * lw + fixed;
+                            T* row = dst + (((size_t)bw * a.H + h) * rows + t) * ld + coff + kc0;
+                            if (kc0 + 8 <= limit) {
+                                st16(row, ld16(Cs + r * LD + c8));
+                            } else {
+                                for (int e = 0; kc0 + e < limit; ++e) row[e] = Cs[r * LD + c8 + e];
+                            }
+                        }
+                    }
+                    continue;  // the next iteration starts with __syncthreads() before Ts / Cs are rewritten
+                }
+            }
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int j = tok0 + warp * 16 + g + (i >> 1) * 8;
                     const int kc = out0 + nt * 8 + tq * 2 + (i & 1);
-                    // ld_pad: tensor-core layouts with padded rows. combined: one array [bias_h | bias_w | 0] per token
-                    // (pre-zeroed by the caller, bias_w == bias_h); otherwise the pad columns are zero-filled here.
-                    const int ld = ld_pad > 0 ? ld_pad : nout;
-                    const int rows = rows_pad > 0 ? rows_pad : a.Wn;
-                    const int coff = (combined && !ymode) ? lh : 0;
-                    if (j < ntok && kc < (combined ? nout : ld)) {
+                    if (j < ntok && kc < limit) {
                         const int t = ymode ? fixed * lw + j : j * lw + fixed;
                         dst[(((size_t)bw * a.H + h) * rows + t) * ld + coff + kc] =
                             ElemTraits<T>::from_float(kc < nout ? s[nt][i] * scale : 0.f);

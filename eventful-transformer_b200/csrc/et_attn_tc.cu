@@ -309,9 +309,15 @@ constexpr int AP_PT = AP_KEYS * QROWS * 2;        // 16 KB: a_state tile [key][r
 constexpr int AP_P = QROWS * AP_KEYS * 2;         // 16 KB: a_n tile (A operand, MN-major) = write-back staging
 constexpr int AP_OFF_ST = 3 * QROWS * 128;        // Q' = three 16 KB blocks: q, 8 bias_h, 8 bias_w
 constexpr int AP_OFF_PT = AP_OFF_ST + 2 * AP_STAGE;
-constexpr int AP_PT_STAGES = 4;                   // a_state tiles are prefetched four tiles ahead by the mover warps
+// a_n tile buffers: 1 = softmax(t+1) publishes only after PV(t) has retired (ping-pong through one buffer); 2 = it may run one
+// tile ahead (the old-state ring gives up one of its four stages to make room) -- build-time experiment switch
+#ifndef ET_APPLY_AN_BUFS
+#define ET_APPLY_AN_BUFS 1
+#endif
+constexpr int AN_BUFS = ET_APPLY_AN_BUFS;
+constexpr int AP_PT_STAGES = AN_BUFS == 1 ? 4 : 3;  // a_state tiles are prefetched this many tiles ahead by the mover warps
 constexpr int AP_OFF_P = AP_OFF_PT + AP_PT_STAGES * AP_PT;
-constexpr int AP_OFF_MISC = AP_OFF_P + AP_P;
+constexpr int AP_OFF_MISC = AP_OFF_P + AN_BUFS * AP_P;
 constexpr int AP_OFF_IDX = AP_OFF_MISC + 1024;    // int32 copy of this batch entry's selected-key index (DELTA mode, k <= AP_IDX_MAX)
 constexpr int AP_IDX_MAX = 3584;                  // 14 KB: what is left of the 227 KB
 constexpr int AP_SMEM = AP_OFF_IDX + AP_IDX_MAX * 4 + 1024;
@@ -335,7 +341,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // MN-major A tiles [64 keys][128 rows]: two 8 KB blocks of 64 rows; key kk = one 128-byte line per block,
     // its 16-byte chunk c (8 rows) stored at chunk position c ^ (kk & 7)
     auto Pt = [&](int u) { return smem + AP_OFF_PT + u * AP_PT; };
-    uint8_t* An = smem + AP_OFF_P;
+    auto An = [&](int t) { return smem + AP_OFF_P + (t % AN_BUFS) * AP_P; };  // a_n tile of key tile t
     auto a_chunk = [](int key, int seg) { return (seg >> 3) * 8192 + key * 128 + (((seg & 7) ^ (key & 7)) << 4); };
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AP_OFF_MISC + 512);
     uint64_t* q_full = bars;
@@ -343,13 +349,13 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint64_t* ps_full = bars + 3;   // [4]: a_state tile landed (128 cp.async arrivals, one per mover thread)
     uint64_t* s_full = bars + 7;
     uint64_t* s_empty = bars + 9;
-    uint64_t* p_ready = bars + 11;  // single a_n buffer: one barrier, one phase per tile (8 softmax warps arrive)
+    uint64_t* p_ready = bars + 20;  // [AN_BUFS]: a_n tile written (8 softmax warps arrive), one phase per use of the buffer
     uint64_t* pv_done = bars + 12;  // [2]: PV MMAs of tile t commit to slot t & 1 (at most one phase outstanding each)
     uint64_t* o_full = bars + 14;
-    uint64_t* an_free = bars + 15;  // a_n tile copied out by the 4 mover warps, one phase per tile
+    uint64_t* an_free = bars + 22;  // [AN_BUFS]: a_n tile copied out by the mover warps
     uint64_t* v_full = bars + 16;   // [2]: V blocks of a stage landed (released by pv_done)
     uint64_t* k_empty = bars + 18;  // [0]: S' MMAs of the pair are complete -> the K' blocks may be reloaded
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * QROWS, h = blockIdx.y, b = blockIdx.z;
@@ -364,8 +370,10 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_kv) : "memory");
         mbar_init(smem_u32(q_full), 1);
         mbar_init(smem_u32(o_full), 1);
-        mbar_init(smem_u32(p_ready), 8);
-        mbar_init(smem_u32(an_free), kMoverWarps);
+        for (int u = 0; u < AN_BUFS; ++u) {
+            mbar_init(smem_u32(&p_ready[u]), 8);
+            mbar_init(smem_u32(&an_free[u]), kMoverWarps);
+        }
         for (int u = 0; u < 2; ++u) {
             mbar_init(smem_u32(&k_full[u]), 1);
             mbar_init(smem_u32(&v_full[u]), 1);
@@ -444,13 +452,13 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     }
                     PF(2);
                 }
-                mbar_wait(smem_u32(p_ready), t & 1);  // every row of the a_n tile is written
+                mbar_wait(smem_u32(&p_ready[t % AN_BUFS]), (t / AN_BUFS) & 1);  // every row of the a_n tile is written
                 PF(3);
                 uint4 wb[MV_CPT];
 #pragma unroll
-                for (int i = 0; i < MV_CPT; ++i) wb[i] = *reinterpret_cast<const uint4*>(An + a_chunk(col0 + MV_CSTEP * i, segi));
+                for (int i = 0; i < MV_CPT; ++i) wb[i] = *reinterpret_cast<const uint4*>(An(t) + a_chunk(col0 + MV_CSTEP * i, segi));
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(an_free));  // all chunks read: the a_n tile may be rewritten
+                if (lane == 0) mbar_arrive(smem_u32(&an_free[t % AN_BUFS]));  // all chunks read: the a_n tile may be rewritten
                 PF(4);
 #pragma unroll
                 for (int i = 0; i < MV_CPT; ++i)
@@ -552,12 +560,12 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             };
             auto issue_pv = [&](int t) {
                 const int u = t & 1;
-                mbar_wait(smem_u32(p_ready), t & 1);
+                mbar_wait(smem_u32(&p_ready[t % AN_BUFS]), (t / AN_BUFS) & 1);
                 PF(3);
                 mbar_wait(smem_u32(&v_full[u]), (t >> 1) & 1);
                 PF(8);
                 tcgen05_fence_after();
-                const uint64_t dan = umma_smem_desc_mn_a(smem_u32(An));
+                const uint64_t dan = umma_smem_desc_mn_a(smem_u32(An(t)));
                 const uint64_t dv1 = umma_smem_desc_mn(smem_u32(V1(u)));
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)  // 16 keys per step = 16 lines of 128 B (2048 B) in the A and V tiles
@@ -610,7 +618,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         // stmatrix: lane 8 g + j addresses key (32 half + 8 n + j), rows quarter * 32 + 8 g ... + 7
         const int sm_r = quarter * 32 + 8 * (lane >> 3), sm_j = lane & 7;
-        const uint32_t st_addr0 = smem_u32(An) + (sm_r >> 6) * 8192 + (half * 32 + sm_j) * 128 + ((((sm_r >> 3) & 7) ^ sm_j) << 4);
+        const uint32_t st_addr0 = smem_u32(smem + AP_OFF_P) + (sm_r >> 6) * 8192 + (half * 32 + sm_j) * 128 + ((((sm_r >> 3) & 7) ^ sm_j) << 4);
         // previous accumulator values of this thread's output slice: loaded now, consumed in the epilogue
         uint16_t* acc = static_cast<uint16_t*>(a.acc);
         uint16_t* out = static_cast<uint16_t*>(a.out);
@@ -660,18 +668,20 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 }
             }
             PF(2);
-            if (t >= 1) {
-                // the a_n tile of t-1 has been consumed by the PV MMAs and copied out by the write-back warps
-                mbar_wait(smem_u32(&pv_done[(t - 1) & 1]), ((t - 1) >> 1) & 1);
-                if (MODE != ET_ATTN_DENSE) mbar_wait(smem_u32(an_free), (t - 1) & 1);
+            if (t >= AN_BUFS) {
+                // the previous tile in this a_n buffer has been consumed by the PV MMAs and copied out by the write-back warps
+                const int tp = t - AN_BUFS;
+                mbar_wait(smem_u32(&pv_done[tp & 1]), (tp >> 1) & 1);
+                if (MODE != ET_ATTN_DENSE) mbar_wait(smem_u32(&an_free[tp % AN_BUFS]), (tp / AN_BUFS) & 1);
             }
             PF(3);
 #pragma unroll
-            for (int n = 0; n < 4; ++n) stmatrix_x4_trans(st_addr0 + n * 1024, fr[n][0], fr[n][1], fr[n][2], fr[n][3]);
+            for (int n = 0; n < 4; ++n)
+                stmatrix_x4_trans(st_addr0 + (t % AN_BUFS) * AP_P + n * 1024, fr[n][0], fr[n][1], fr[n][2], fr[n][3]);
             PF(4);
             fence_proxy_async();  // generic-proxy smem writes -> visible to tcgen05.mma
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(p_ready));
+            if (lane == 0) mbar_arrive(smem_u32(&p_ready[t % AN_BUFS]));
             PF(5);
         }
         PF(11);
