@@ -25,7 +25,7 @@ VITDET_B = dict(  # configs/models/vitdet_b_coco.yml
 
 
 def backbone_kwargs(cfg, input_size, block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
-                    matmul_2_cast=None, has_class_token=False, pool_size=None):
+                    matmul_2_cast=None, has_class_token=False, pool_size=None, ats_fraction=None):
     """kwargs for ViTBackbone(...) in the shape configs/models/*.yml feeds it (backbones.py:13-24)."""
     block_config = dict(dim=cfg["dim"], heads=cfg["heads"], mlp_ratio=cfg["mlp_ratio"])
     if cfg.get("relative_embedding_size") is not None:
@@ -36,6 +36,8 @@ def backbone_kwargs(cfg, input_size, block_class="EventfulBlock", windowed_class
         block_config["matmul_2_cast"] = matmul_2_cast
     if pool_size is not None:
         block_config["pool_size"] = list(pool_size)
+    if ats_fraction is not None:
+        block_config["ats_fraction"] = ats_fraction
     kw = dict(
         block_config=block_config,
         depth=cfg["depth"],

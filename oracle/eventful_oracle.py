@@ -285,7 +285,9 @@ class OracleBackbone:
     EventfulMatmul1Block / EventfulBlock (blocks.py:26-575) as plain functions
     over a parameter dict that uses the reference's state-dict key names and a
     per-block state dict.  K/V pooling (blocks.py:303-326,525-540) is restated
-    (`pool_size`); ATS (blocks.py:150-181) is not.
+    (`pool_size`), and so is adaptive token sampling (`ats_fraction`, blocks.py:150-181,196-203,378-391) with the
+    reference's exact axis handling: the per-head scores are summed over the BATCH axis and row h of the resulting index
+    serves batch entry h, so it is only defined -- in the reference too -- when batch == heads.
     """
 
     def __init__(
@@ -309,6 +311,7 @@ class OracleBackbone:
         stgt=False,
         pool_size=None,
         windowed_pool_size="same",
+        ats_fraction=None,
     ):
         self.w = params
         self.depth, self.dim, self.heads = depth, dim, heads
@@ -333,7 +336,9 @@ class OracleBackbone:
             if windowed and windowed_pool_size != "same":
                 pool = windowed_pool_size
             pool = None if pool is None else tuple(pool)
-            self.blocks.append(dict(cls=cls, window=ws, rel=rel, cast=cast, pool=pool))
+            if ats_fraction is not None:  # blocks.py:71-74
+                assert pool is None and ws is None and 0.0 <= ats_fraction <= 1.0
+            self.blocks.append(dict(cls=cls, window=ws, rel=rel, cast=cast, pool=pool, ats=ats_fraction))
         self.policy = None
         self.record_free = False
         self.reset()
@@ -465,20 +470,75 @@ class OracleBackbone:
             a, v = a.to(dt), v.to(dt)
         return a, v, old
 
+    # -- adaptive token sampling ------------------------------------------------------
+    def _ats(self, i, a, v, forced=None):
+        """
+        Block._adaptive_token_sampling (blocks.py:150-181): the top-k variant of ATS.  a: (B, H, N, N) attention
+        probabilities, v: (B, H, N, dh).  Returns (rows of `a` kept, index (B', n_select)) or (a, None).
+        score[b, h, t] = a[b, h, t, 0] * |v[b, h, t]|, divided by its sum over t >= 1 (:155-157); the class token always
+        wins (:160); the scores are then summed over axis -3 (:163) -- for the (B, H, N) score tensor of a 3-D block
+        input that is the batch axis -- and the n_select best tokens per remaining row are kept, sorted and stabilised
+        against the previous frame's set (:168-176).  The gather at :179 broadcasts index row r to batch entry r, which
+        requires the index to have B rows, i.e. B == H (torch raises otherwise, and so does this restatement).
+        `forced[(i, "ats")]`: replay a given stabilised index instead of selecting (parity at identical index sets).
+        """
+        frac = self.blocks[i]["ats"]
+        if frac is None:
+            return a, None
+        st = self._st(i, "ats")
+        if forced is not None and (i, "ats") in forced:
+            index = forced[(i, "ats")].clone()
+        else:
+            raw = a[..., 0] * torch.linalg.vector_norm(v, dim=-1)
+            score = raw / raw[..., 1:].sum(dim=-1, keepdim=True)
+            score[..., 0] = float("inf")
+            score = score.sum(dim=-3)
+            n_select = int(frac * (score.shape[-1] - 1)) + 1  # :165
+            index = score.topk(n_select, sorted=False)[1].sort(dim=-1)[0]  # :168, :379
+            index = self._stabilize(st.get("last"), index)
+        st["last"] = index
+        self.trace.append(((i, "ats"), index))
+        if index.shape[:-1] != a.shape[:1]:
+            raise RuntimeError(f"ATS index has {tuple(index.shape[:-1])} rows for a batch of {a.shape[0]} "
+                               "(the reference's gather, blocks.py:179, needs batch == heads)")
+        rows = index.view(index.shape[0], 1, index.shape[-1], 1).expand(-1, a.shape[1], -1, a.shape[-1])
+        return a.gather(-2, rows), index
+
+    @staticmethod
+    def _stabilize(last, index):
+        """Block._stabilize_ats_indices (blocks.py:378-391): tokens that stay keep their slot of the previous frame's
+        index; the slots of tokens that left are filled, in order, with the tokens that entered."""
+        if last is None:
+            return index
+        out = last.clone()
+        for r in range(index.shape[0]):
+            left = ~torch.isin(last[r], index[r])
+            entered = ~torch.isin(index[r], last[r])
+            out[r, left] = index[r, entered]
+        return out
+
+    @staticmethod
+    def _ats_skip(skip, index):
+        """Block._gather_ats_skip (blocks.py:196-203)."""
+        if index is None:
+            return skip
+        return skip.gather(-2, index.unsqueeze(-1).expand(-1, -1, skip.shape[-1]))
+
     # -- attention variants --------------------------------------------------------
-    def _attention_dense(self, i, x):
-        """Block._forward_attention (blocks.py:205-240), ATS off."""
+    def _attention_dense(self, i, x, forced=None):
+        """Block._forward_attention (blocks.py:205-240)."""
         x = self._partition_windows(i, x)
         q, k, v = self._heads(x)
         k, v = self._pool_tokens(i, k), self._pool_tokens(i, v)  # :216-217
         a = (q / self.scale) @ k.transpose(-2, -1)  # :223
         a = self._relpos(i, a, q, inplace=True)  # :225
         a = a.softmax(dim=-1)  # :226
+        a, ats = self._ats(i, a, v, forced)  # :229
         a, v, old = self._cast(self.blocks[i]["cast"], a, v)  # :231
         x = a @ v  # :232
         x = self._merge_heads(x)
         x = self._recombine_windows(i, x)
-        return x.to(old) if self.blocks[i]["cast"] is not None else x
+        return (x.to(old) if self.blocks[i]["cast"] is not None else x), ats
 
     def _matmul_1(self, i, x, index):
         """EventfulMatmul1Block._forward_matmul_1 (blocks.py:506-523)."""
@@ -491,18 +551,20 @@ class OracleBackbone:
         a = self._relpos(i, a, q, inplace=False)  # :521
         return a.softmax(dim=-1), v, index_k
 
-    def _attention_matmul1(self, i, x, index):
+    def _attention_matmul1(self, i, x, index, forced=None):
         """EventfulMatmul1Block._forward_attention (blocks.py:497-504)."""
         a, v, _ = self._matmul_1(i, x, index)
+        a, ats = self._ats(i, a, v, forced)  # :499
         a, v, old = self._cast(self.blocks[i]["cast"], a, v)
         x = self._merge_heads(a @ v)
-        return x.to(old) if self.blocks[i]["cast"] is not None else x
+        return (x.to(old) if self.blocks[i]["cast"] is not None else x), ats
 
-    def _attention_eventful(self, i, x, index):
+    def _attention_eventful(self, i, x, index, forced=None):
         """EventfulBlock._forward_attention (blocks.py:558-575)."""
         a, v, index_k = self._matmul_1(i, x, index)
         cast = self.blocks[i]["cast"]
         a, v, old = self._cast(cast, a, v)  # :561
+        a, ats = self._ats(i, a, v, forced)  # :562 (after the cast: the scores are computed in the cast dtype)
         if not cast:
             v = v.clone()  # :563-566
         v_n, v_d, index_v = token_gate(self._st(i, "v_gate"), v, forced_index=index_k, delta=True)
@@ -511,14 +573,15 @@ class OracleBackbone:
         )
         x = delta_accumulator(self._st(i, "matmul_accumulator_2"), a_n, v_n, a_d, v_d)  # :569
         x = self._merge_heads(x)  # :573
-        return x.to(old) if cast is not None else x
+        return (x.to(old) if cast is not None else x), ats
 
     # -- blocks ----------------------------------------------------------------------
-    def _block_dense(self, i, x):
+    def _block_dense(self, i, x, forced=None):
         """Block.forward (blocks.py:117-137)."""
         skip = x
         x = self._linear(i, "qkv", self._ln(i, "input_layer_norm", x))
-        x = self._attention_dense(i, x)
+        x, ats = self._attention_dense(i, x, forced)
+        skip = self._ats_skip(skip, ats)  # :126
         x = self._linear(i, "projection", x) + skip
         skip = x
         x = self._linear(i, "mlp_1", self._ln(i, "mlp_layer_norm", x))
@@ -541,11 +604,12 @@ class OracleBackbone:
         x = self._linear(i, "qkv", x)  # :462
         x = token_buffer(self._st(i, "qkv_accumulator"), x, index)  # :424
         if cls == TOKENWISE:
-            x = self._attention_dense(i, x)
+            x, ats = self._attention_dense(i, x, forced)
         elif cls == MATMUL1:
-            x = self._attention_matmul1(i, x, index)
+            x, ats = self._attention_matmul1(i, x, index, forced)
         else:
-            x = self._attention_eventful(i, x, index)
+            x, ats = self._attention_eventful(i, x, index, forced)
+        skip = self._ats_skip(skip, ats)  # :426, :493
         x, index = self._gate(i, "projection_gate", x, forced)  # :432
         x = self._linear(i, "projection", x)
         x = token_buffer(self._st(i, "projection_accumulator"), x, index)
@@ -581,7 +645,7 @@ class OracleBackbone:
         x = x + self._pos
         for i in range(self.depth):
             if self.blocks[i]["cls"] == DENSE:
-                x = self._block_dense(i, x)
+                x = self._block_dense(i, x, forced)
             else:
                 x = self._block_gated(i, x, forced)
         return x

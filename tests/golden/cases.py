@@ -81,6 +81,19 @@ CASES = {
     "vitdet_b_1024": dict(cfg=VITDET_B_FULL, input_size=(64, 64), batch=1, frames=4, policy=("topk", dict(k=2048)),
                           block_class="EventfulBlock", windowed_class="EventfulTokenwiseBlock",
                           std=0.02, stream="drift", seed=17, subsample=True),
+    # Adaptive token sampling (configs/evaluate/vivit_epic_kitchens/_ats.yml): class token, no windows / rel-pos.  The
+    # reference's ATS code only runs when batch == heads (blocks.py:163 sums the scores over dim -3, which is the BATCH
+    # axis of the (batch, heads, tokens) scores of a 3-D block input, and the per-head index rows are then used per batch
+    # entry; ViViT-B meets that by coincidence: 12 batched views, 12 heads), so these cases use batch = heads = 2.
+    "tiny_ats_dense": dict(cfg=TINY_GLOBAL, input_size=(4, 4), batch=2, frames=3, policy=None, block_class="Block",
+                           windowed_class=None, has_class_token=True, ats_fraction=0.7, std=0.08, stream="drift", seed=20),
+    "tiny_ats_eventful": dict(cfg=TINY_GLOBAL, input_size=(4, 4), batch=2, frames=5, policy=("fraction", dict(fraction=0.5)),
+                              block_class="EventfulBlock", has_class_token=True, ats_fraction=0.7, std=0.08,
+                              stream="drift", seed=21),
+    # the temporal_ats configuration (configs/evaluate/vivit_epic_kitchens/temporal_ats_200.yml): fp16 attention-value path
+    "tiny_ats_cast16": dict(cfg=TINY_GLOBAL, input_size=(4, 4), batch=2, frames=5, policy=("fraction", dict(fraction=0.5)),
+                            block_class="EventfulBlock", has_class_token=True, ats_fraction=0.7, matmul_2_cast="float16",
+                            std=0.08, stream="drift", seed=22),
 }
 
 GATES = ("qkv_gate", "projection_gate", "mlp_gate")

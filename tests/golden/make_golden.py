@@ -52,7 +52,7 @@ def reference_backbone(case):
         cfg, case["input_size"], block_class=case["block_class"],
         windowed_class=case.get("windowed_class", "EventfulTokenwiseBlock"),
         matmul_2_cast=case.get("matmul_2_cast"), has_class_token=case.get("has_class_token", False),
-        pool_size=case.get("pool_size"),
+        pool_size=case.get("pool_size"), ats_fraction=case.get("ats_fraction"),
     )
     if kw.get("windowed_class") is None:
         kw.pop("windowed_class", None)
@@ -112,6 +112,9 @@ def run_case(name, case):
             for (i, gate), index in trace.items():
                 blob[f"idx_{t}_{i}_{gate}"] = np.sort(index.numpy(), axis=-1).astype(np.int32)
                 blob[f"raw_{t}_{i}_{gate}"] = index.numpy().astype(np.int32)  # the reference's own order
+            for i, block in enumerate(model.blocks):  # ATS: the stabilised token indices of every block (blocks.py:175-176)
+                if getattr(block, "last_ats_indices", None) is not None:
+                    blob[f"ats_{t}_{i}"] = block.last_ats_indices.numpy().astype(np.int32)
             counts = model.total_counts()
             for key, value in counts.items():
                 blob[f"count_{t}_{key}"] = np.int64(value)

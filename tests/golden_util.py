@@ -39,7 +39,7 @@ def oracle_for(case, params):
         matmul_2_cast=case.get("matmul_2_cast"),
         windowed_matmul_2_cast=(None if case.get("matmul_2_cast") else "same"),
         gate_before_ln=case.get("gate_before_ln", False), stgt=case.get("stgt", False),
-        pool_size=case.get("pool_size"),
+        pool_size=case.get("pool_size"), ats_fraction=case.get("ats_fraction"),
         windowed_pool_size=(None if case.get("pool_size") else "same"),  # configs/*/vitdet_vid/_spatial.yml
     )
     if case["policy"] is not None:

@@ -22,6 +22,16 @@ def _forced_from(gold, t):
     return forced
 
 
+def _check_ats(model, gold, t):
+    """Adaptive token sampling: the stabilised index of every block equals the reference's, slot by slot."""
+    seen = 0
+    for (i, gate), index in model.trace:
+        if gate == "ats":
+            assert np.array_equal(index.numpy(), gold[f"ats_{t}_{i}"]), (t, i)
+            seen += 1
+    assert seen == sum(1 for f in gold.files if f.startswith(f"ats_{t}_"))
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_oracle_bitwise_given_reference_index_order(name):
     """Replaying the reference's own selection order, fp32 activations are bit-identical."""
@@ -35,6 +45,7 @@ def test_oracle_bitwise_given_reference_index_order(name):
             got = subsample(y) if case.get("subsample") else y
             assert torch.equal(got, torch.from_numpy(gold[f"out_{t}"])), (name, t)
             assert float(y.double().abs().sum()) == float(gold[f"out_abs_sum_{t}"])
+            _check_ats(model, gold, t)
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -53,8 +64,11 @@ def test_oracle_matches_reference_fixture(name):
             assert got.shape == want.shape
             tol = 2e-5 * max(1.0, float(want.abs().max()))
             assert (got - want).abs().max() <= tol, f"{name} frame {t}: {(got - want).abs().max()}"
+            _check_ats(model, gold, t)
             seen = 0
             for (i, gate), index in model.trace:
+                if gate == "ats":
+                    continue
                 key = f"idx_{t}_{i}_{gate}"
                 assert key in gold.files
                 assert np.array_equal(np.sort(index.numpy(), axis=-1), gold[key]), key
