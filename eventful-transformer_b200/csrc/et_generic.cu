@@ -166,6 +166,11 @@ struct GenArgs {
     const void* dV;  // (B, kmax, D) state dtype
     const void* Vr;  // (B, kmax, D) state dtype
     int dt, sdt;     // model dtype, state dtype
+    float* ats_raw;  // optional (B, H, Nq): adaptive-token-sampling raw scores a[b, h, t, 0] * |v[b, h, t]| (gen_stats_kernel)
+    int ats_dt;      // dtype the reference holds a and v in at that point (model dtype, or the matmul_2_cast dtype)
+    int stats_only;  // launch_generic: statistics pass only
+    const long long* q_index;  // optional (B, Nq): query row t of batch entry b is row q_index[b][t] of q (adaptive token sampling)
+    int q_batch_rows;          // rows per batch entry of the q tensor (Nq unless q_index selects among more rows)
 };
 
 // window-local token -> global token row, or -1 for padding
@@ -184,8 +189,9 @@ __device__ __forceinline__ void load_queries(const GenArgs& a, int b, int h, int
         float v = 0.f;
         const int t = q0 + r;
         if (t < a.Wn && c < a.dh) {
-            const int tok = map_token(a, win, t);
-            v = tok >= 0 ? ld_elem(a.q, ((long long)b * a.Nq + tok) * a.ldq + h * a.dh + c, a.dt)
+            int tok = map_token(a, win, t);
+            if (a.q_index != nullptr) tok = (int)a.q_index[(long long)b * a.Nq + t];
+            v = tok >= 0 ? ld_elem(a.q, ((long long)b * a.q_batch_rows + tok) * a.ldq + h * a.dh + c, a.dt)
                          : ld_elem(a.pad, h * a.dh + c, a.dt);
         }
         Qt[c * LDT + r] = v;
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(ATHREADS) gen_stats_kernel(const GenArgs a) {
     const int b = blockIdx.z / nwin, win = blockIdx.z - b * nwin;
     load_queries(a, b, h, win, q0, Qt, bh, bw);
     const int nkeys = a.windowed ? a.Wn : a.Nk;
-    float mrow[4], lrow[4];
+    float mrow[4], lrow[4], s_cls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 4; ++i) { mrow[i] = -INFINITY; lrow[i] = 0.f; }
     for (int key0 = 0; key0 < nkeys; key0 += TK) {
@@ -282,6 +288,10 @@ __global__ void __launch_bounds__(ATHREADS) gen_stats_kernel(const GenArgs a) {
         __syncthreads();
         float s[4][4];
         score_tile(a, Qt, Kt, bh, bw, s_tok, ty, tx, s);
+        if (key0 == 0 && tx == 0) {  // logit of key 0 (the class token) for the ATS scores
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s_cls[i] = s[i][0];
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float mx = fmaxf(fmaxf(s[i][0], s[i][1]), fmaxf(s[i][2], s[i][3]));
@@ -305,6 +315,17 @@ __global__ void __launch_bounds__(ATHREADS) gen_stats_kernel(const GenArgs a) {
                 float* st = a.stats + (((size_t)blockIdx.z * a.H + h) * a.Wn + t) * 2;
                 st[0] = mrow[i];
                 st[1] = lrow[i];
+                if (a.ats_raw != nullptr) {
+                    // Block._adaptive_token_sampling (blocks.py:154-155): class_scores * |v|, every factor rounded where the
+                    // reference holds it in a 16-bit dtype (softmax in the model dtype, then a and v cast to ats_dt)
+                    const float a0 = round_dt(round_dt(expf(s_cls[i] - mrow[i]) / lrow[i], a.dt), a.ats_dt);
+                    float ss = 0.f;
+                    for (int c = 0; c < a.dh; ++c) {
+                        const float v = round_dt(ld_elem(a.vv, ((long long)b * a.Nk + t) * a.ldkv + h * a.dh + c, a.dt), a.ats_dt);
+                        ss = fmaf(v, v, ss);
+                    }
+                    a.ats_raw[((size_t)b * a.H + h) * a.Nq + t] = round_dt(a0 * round_dt(sqrtf(ss), a.ats_dt), a.ats_dt);
+                }
             }
         }
     }
@@ -549,6 +570,7 @@ int launch_generic(const GenArgs& a, cudaStream_t s) {
     if ((rc = et_raise_smem(gen_stats_kernel, sa))) return rc;
     et_launch(gen_stats_kernel, grid, dim3(ATHREADS), sa, s, a);
     ET_COUNT_LAUNCH(1);
+    if (a.stats_only) return ET_OK;
     const int sb = apply_smem(a.mode, kh, kw);
     if (a.mode == ET_ATTN_DELTA) {
         if ((rc = et_raise_smem(gen_apply_kernel<ET_ATTN_DELTA>, sb))) return rc;
@@ -604,19 +626,23 @@ int et_generic_window_attention(const void* qkv, const void* pad_token, const vo
         a.nwx = a.nwy = 1; a.Wn = N; a.aw = gw; a.kh = gh; a.kw = gw;
     }
     a.rscale = 1.0f / sqrtf((float)dh);
-    a.mode = ET_ATTN_DENSE; a.out = out; a.stats = stats; a.dt = dtype; a.sdt = dtype; a.NP = 0;
+    a.mode = ET_ATTN_DENSE; a.out = out; a.stats = stats; a.dt = dtype; a.sdt = dtype; a.NP = 0; a.q_batch_rows = N;
     return launch_generic(a, s);
 }
 
 // Global attention (DENSE / FIRST / DELTA) with optional pooled K/V, separate state dtype and device-side counts.
-int et_generic_global_attention(const void* qkv, const void* kv_pooled, int pool_h, int pool_w, const void* rel_y,
-                                const void* rel_x, int mode, const int64_t* idx, const int32_t* count, int k, void* a_state,
-                                void* v_state, void* acc, void* out, float* stats, void* ws, int B, int N, int gh, int gw,
-                                int H, int dh, int dtype, int state_dtype, cudaStream_t s) {
+// `q_index` != null (adaptive token sampling): the Nq query rows are the tokens q_index[b][0 .. Nq) of qkv instead of all N;
+// keys and values are still the N tokens of qkv, the state / accumulator / output have Nq rows.
+static int generic_global_impl(const void* qkv, const void* kv_pooled, int pool_h, int pool_w, const void* rel_y,
+                               const void* rel_x, int mode, const int64_t* idx, const int32_t* count, int k, void* a_state,
+                               void* v_state, void* acc, void* out, float* stats, void* ws, int B, int N, int gh, int gw,
+                               int H, int dh, int dtype, int state_dtype, cudaStream_t s, const long long* q_index, int Nq) {
     GenArgs a = {};
     const int D = H * dh;
     a.q = qkv; a.ldq = 3LL * D; a.rel_y = rel_y; a.rel_x = rel_x;
     a.B = B; a.Nq = N; a.H = H; a.dh = dh; a.D = D; a.gh = gh; a.gw = gw; a.windowed = 0; a.nwx = a.nwy = 1; a.Wn = N; a.aw = gw;
+    a.q_batch_rows = N;
+    if (q_index != nullptr) { a.q_index = q_index; a.Nq = Nq; a.Wn = Nq; }
     if (kv_pooled != nullptr) {
         a.kk = kv_pooled;
         a.vv = static_cast<const char*>(kv_pooled) + (size_t)D * elem_size(dtype);
@@ -628,7 +654,7 @@ int et_generic_global_attention(const void* qkv, const void* kv_pooled, int pool
     }
     a.rscale = 1.0f / sqrtf((float)dh);
     a.mode = mode; a.idx = reinterpret_cast<const long long*>(idx); a.count = count; a.kmax = mode == ET_ATTN_DELTA ? k : 0;
-    a.a_state = a_state; a.NP = (N + 7) / 8 * 8; a.acc = acc; a.out = out; a.stats = stats; a.dt = dtype; a.sdt = state_dtype;
+    a.a_state = a_state; a.NP = (a.Nq + 7) / 8 * 8; a.acc = acc; a.out = out; a.stats = stats; a.dt = dtype; a.sdt = state_dtype;
     if (mode == ET_ATTN_DELTA) {
         if (k == 0) return ET_OK;
         char* w = static_cast<char*>(ws);
@@ -648,7 +674,58 @@ int et_generic_global_attention(const void* qkv, const void* kv_pooled, int pool
     return launch_generic(a, s);
 }
 
+int et_generic_global_attention(const void* qkv, const void* kv_pooled, int pool_h, int pool_w, const void* rel_y,
+                                const void* rel_x, int mode, const int64_t* idx, const int32_t* count, int k, void* a_state,
+                                void* v_state, void* acc, void* out, float* stats, void* ws, int B, int N, int gh, int gw,
+                                int H, int dh, int dtype, int state_dtype, cudaStream_t s) {
+    return generic_global_impl(qkv, kv_pooled, pool_h, pool_w, rel_y, rel_x, mode, idx, count, k, a_state, v_state, acc, out, stats,
+                               ws, B, N, gh, gw, H, dh, dtype, state_dtype, s, nullptr, 0);
+}
+
 extern "C" {
+
+int et_ats_scores(const void* qkv, int64_t B, int64_t N, int64_t heads, int64_t dh, int dtype, int score_dtype, float* row_stats,
+                  float* raw_scores, void* stream) {
+    ET_CHECK_ARG(qkv && row_stats && raw_scores, "et_ats_scores: null pointer");
+    ET_CHECK_ARG(B > 0 && N > 0 && heads > 0 && dh > 0 && dh <= 64, "et_ats_scores: bad shape (head dim <= 64)");
+    ET_CHECK_ARG((dtype == ET_F32 || dtype == ET_BF16 || dtype == ET_F16) &&
+                     (score_dtype == ET_F32 || score_dtype == ET_BF16 || score_dtype == ET_F16), "et_ats_scores: bad dtype");
+    GenArgs a = {};
+    const int D = (int)(heads * dh);
+    a.q = qkv; a.ldq = 3LL * D;
+    a.kk = static_cast<const char*>(qkv) + (size_t)D * elem_size(dtype);
+    a.vv = static_cast<const char*>(qkv) + (size_t)2 * D * elem_size(dtype);
+    a.ldkv = 3LL * D;
+    a.B = (int)B; a.Nq = a.Nk = a.Wn = (int)N; a.H = (int)heads; a.dh = (int)dh; a.D = D; a.nwx = a.nwy = 1;
+    a.rscale = 1.0f / sqrtf((float)dh);
+    a.mode = ET_ATTN_DENSE; a.stats = row_stats; a.dt = dtype; a.sdt = score_dtype; a.q_batch_rows = (int)N;
+    a.ats_raw = raw_scores; a.ats_dt = score_dtype; a.stats_only = 1;
+    int rc = launch_generic(a, et_stream(stream));
+    if (rc) return rc;
+    ET_CHECK_LAUNCH("et_ats_scores");
+    return ET_OK;
+}
+
+int et_global_attention_rows(const void* qkv, const int64_t* q_index, int64_t Nq, int mode, const int64_t* idx,
+                             const int32_t* count, int64_t k, void* a_state, void* v_state, void* acc, void* out,
+                             float* row_stats, void* workspace, int64_t B, int64_t N, int64_t heads, int64_t dh, int dtype,
+                             int state_dtype, void* stream) {
+    ET_CHECK_ARG(q_index && qkv && out && row_stats, "et_global_attention_rows: null pointer");
+    ET_CHECK_ARG((dtype == ET_F32 || dtype == ET_BF16 || dtype == ET_F16) &&
+                     (state_dtype == ET_F32 || state_dtype == ET_BF16 || state_dtype == ET_F16), "et_global_attention_rows: bad dtype");
+    ET_CHECK_ARG(mode == ET_ATTN_DENSE || mode == ET_ATTN_FIRST || mode == ET_ATTN_DELTA, "et_global_attention_rows: bad mode");
+    ET_CHECK_ARG(B > 0 && N > 0 && Nq > 0 && Nq <= N && heads > 0 && dh > 0 && dh <= 64,
+                 "et_global_attention_rows: bad shape (Nq <= N, head dim <= 64)");
+    ET_CHECK_ARG(mode == ET_ATTN_DENSE || (a_state && v_state && acc), "et_global_attention_rows: state pointers required");
+    ET_CHECK_ARG(mode != ET_ATTN_DELTA || (idx != nullptr && k >= 0 && k <= N && workspace != nullptr),
+                 "et_global_attention_rows: DELTA needs idx, k <= N and the workspace");
+    int rc = generic_global_impl(qkv, nullptr, 1, 1, nullptr, nullptr, mode, idx, count, (int)k, a_state, v_state, acc, out,
+                                 row_stats, workspace, (int)B, (int)N, 0, 0, (int)heads, (int)dh, dtype, state_dtype,
+                                 et_stream(stream), reinterpret_cast<const long long*>(q_index), (int)Nq);
+    if (rc) return rc;
+    ET_CHECK_LAUNCH("et_global_attention_rows");
+    return ET_OK;
+}
 
 int et_pool_kv(const void* qkv, void* out, int64_t B, int64_t gh, int64_t gw, int64_t D, int64_t pool_h, int64_t pool_w,
                int dtype, void* stream) {

@@ -52,6 +52,10 @@ _SIGNATURES = {
     "et_global_attention": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                     c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                     c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "et_ats_scores": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "et_global_attention_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                         c_int, c_int, c_void_p]),
     "et_patchify": (c_int, [c_void_p, c_void_p] + [c_int64] * 8 + [c_int, c_void_p]),
     "et_pool_kv": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "et_pool_index": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
@@ -398,6 +402,50 @@ def global_attention(qkv, heads, grid, mode, rel=None, idx=None, a_state=None, v
     _check(lib().et_global_attention(_p(qkv), _p(kv_pooled), ph, pw, _p(rel_y), _p(rel_x), int(mode), _p(idx), _p(count), k,
                                      _p(a_state), _p(v_state), _p(acc), _p(out), _p(stats), _p(ws), b, n, gh, gw, heads,
                                      dh, dtype_code(qkv), sdt, _stream()), "et_global_attention")
+    return out
+
+
+def ats_scores(qkv, heads, score_dtype=None):
+    """Adaptive token sampling, scoring pass: raw[b, h, t] = softmax(q k^T / sqrt(dh))[b, h, t, 0] * |v[b, h, t]| as a
+    (B, H, N) tensor of `score_dtype` (the dtype the reference holds a and v in at that point; default: the model's)."""
+    require_device(qkv)
+    _dense(qkv, "qkv")
+    b, n, d3 = qkv.shape
+    dh = d3 // 3 // heads
+    score_dtype = qkv.dtype if score_dtype is None else score_dtype
+    stats = torch.empty((b, heads, n, 2), dtype=torch.float32, device=qkv.device)
+    raw = torch.empty((b, heads, n), dtype=torch.float32, device=qkv.device)
+    _check(lib().et_ats_scores(_p(qkv), b, n, heads, dh, dtype_code(qkv), _DTYPES[score_dtype], _p(stats), _p(raw), _stream()),
+           "et_ats_scores")
+    return raw.to(score_dtype)  # exact: every value was rounded to score_dtype by the kernel
+
+
+def global_attention_rows(qkv, q_index, heads, mode, idx=None, a_state=None, v_state=None, acc=None, stats=None, count=None,
+                          state_dtype=None):
+    """et_global_attention for the query tokens q_index (B, Nq) only (adaptive token sampling): keys and values are all N
+    tokens of qkv (B, N, 3D); a_state (B, H, N, NP(Nq)), acc / out (B, Nq, D)."""
+    require_device(qkv)
+    _dense(qkv, "qkv"), _dense(q_index, "query index")
+    b, n, d3 = qkv.shape
+    d = d3 // 3
+    dh = d // heads
+    nq = q_index.shape[-1]
+    if q_index.shape[0] != b or q_index.dtype != torch.int64:
+        raise ValueError("eventful_b200.global_attention_rows: the query index must be (B, Nq) int64")
+    k = 0 if idx is None else idx.shape[-1]
+    if mode == ATTN_DELTA and k == 0:
+        return acc.to(qkv.dtype)
+    out = torch.empty((b, nq, d), dtype=qkv.dtype, device=qkv.device)
+    if stats is None:
+        stats = torch.empty((b, heads, nq, 2), dtype=torch.float32, device=qkv.device)
+    sdt = _DTYPES[qkv.dtype if state_dtype is None else state_dtype]
+    ws = attn_workspace(b, n, 0, 0, 0, 0, heads, dh, 2 * k if sdt == ET_F32 else k, False, qkv.device)
+    for t, name in ((idx, "index"), (a_state, "A-gate state"), (v_state, "v-gate state"), (acc, "accumulator")):
+        if t is not None:
+            _dense(t, name)
+    _check(lib().et_global_attention_rows(_p(qkv), _p(q_index), nq, int(mode), _p(idx), _p(count), k, _p(a_state), _p(v_state),
+                                          _p(acc), _p(out), _p(stats), _p(ws), b, n, heads, dh, dtype_code(qkv), sdt, _stream()),
+           "et_global_attention_rows")
     return out
 
 

@@ -93,6 +93,8 @@ class ViTBackbone(ExtendedModule):
             return False  # frame 0 is the dense flush, frame 1 warms up the incremental path
         if any(m.count_mode for m in self.extended_modules()):
             return False
+        if any(getattr(block, "ats_fraction", None) is not None for block in self.blocks):
+            return False  # adaptive token sampling stabilises its index on the host every frame (as the reference does)
         return self._policy_key(x.shape[-2]) is not None
 
     def _forward_graph(self, x):

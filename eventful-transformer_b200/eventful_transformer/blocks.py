@@ -22,7 +22,10 @@ capturable too.
 
 Variants: K/V pooling (pool_size; global blocks), matmul_2_cast different from
 the model dtype and fp32 models run on the general-precision kernels (csrc/et_generic.cu).
-Not implemented: adaptive token sampling (ats_fraction), drop-path in training mode.
+Adaptive token sampling (ats_fraction, blocks.py:150-181 of the reference): et_ats_scores emits the per-head token
+scores, the tiny (B, H, N) normalise / sum / top-k / stabilise step runs on the host side exactly as the reference
+does it (including its axis handling, which needs batch == heads), and attention then runs on the kept query rows only
+(et_global_attention_rows).  Not implemented: drop-path in training mode.
 """
 
 import os
@@ -91,11 +94,15 @@ class Block(ExtendedModule):
             assert pool_size is None
             assert window_size is None
             assert not (ats_fraction < 0.0 or ats_fraction > 1.0)
-            raise NotImplementedError("eventful_b200: adaptive token sampling (ats_fraction) is not implemented yet")
+            if relative_embedding_size is not None:
+                # the reference's own rel-pos tables are sized to the full token grid and no longer match the
+                # pruned token count one block later; no shipped configuration combines the two
+                raise NotImplementedError("eventful_b200: adaptive token sampling with relative position embeddings")
         assert not (drop_path_rate < 0.0 or drop_path_rate > 1.0)
         assert matmul_2_cast in [None, "float16", "bfloat16"]
         self.ats_fraction = ats_fraction
         self.last_ats_indices = None
+        self._ats_now = None
         self.matmul_2_cast = matmul_2_cast
         self.pool_size = None if pool_size is None else numeric_tuple(pool_size, length=2)
         if self.pool_size is not None and window_size is not None:
@@ -136,7 +143,61 @@ class Block(ExtendedModule):
 
     def reset_self(self):
         self.last_ats_indices = None
+        self._ats_now = None
         self._identity = {}
+
+    # ------------------------------------------------------------------ adaptive token sampling
+    def _ats_select(self, qkv, score_dtype):
+        """
+        Block._adaptive_token_sampling (reference blocks.py:150-176) on the QKV buffer: the stabilised index of the
+        tokens whose query rows are kept, (B, n_select) int64.  The raw scores a[..., 0] * |v| come from the
+        statistics kernel; what follows works on a (B, H, N) tensor and is kept in the reference's arithmetic
+        (same dtype, same reductions): divide by the sum over the non-class tokens, pin the class token, sum over
+        axis -3, keep the int(fraction * (N - 1)) + 1 best, sort, stabilise.  Axis -3 of the 3-D score tensor is the
+        BATCH axis and row h of the result is then used for batch entry h: defined for batch == heads only (the
+        reference raises in .gather() otherwise; ViViT-B runs it with 12 batched views and 12 heads).
+        """
+        raw = native.ats_scores(qkv, self.heads, score_dtype)
+        score = raw / raw[..., 1:].sum(dim=-1, keepdim=True)
+        score[..., 0] = float("inf")
+        score = score.sum(dim=-3)
+        n_select = int(self.ats_fraction * (score.shape[-1] - 1)) + 1
+        index = score.topk(n_select, sorted=False)[1].sort(dim=-1)[0]
+        if index.shape[0] != qkv.shape[0]:
+            raise RuntimeError(f"eventful_b200: adaptive token sampling yields {index.shape[0]} index rows (one per head) "
+                               f"for a batch of {qkv.shape[0]}; the reference's gather (blocks.py:179) needs batch == heads")
+        index = self._stabilize_ats_indices(index)
+        self.last_ats_indices = self._ats_now = index
+        return index
+
+    def _stabilize_ats_indices(self, index):
+        """Tokens that stay keep last frame's slot; slots of the tokens that left take the new tokens in ascending
+        order (reference blocks.py:378-391, a host-side loop there too)."""
+        if self.last_ats_indices is None:
+            return index
+        new, old = index.cpu(), self.last_ats_indices.cpu()
+        out = old.clone()
+        for r in range(new.shape[0]):
+            out[r, ~torch.isin(old[r], new[r])] = new[r, ~torch.isin(new[r], old[r])]
+        return out.to(index.device)
+
+    def _ats_rows(self, x):
+        """x[b, ats_index[b]]: the kept rows of a (B, N, C) tensor (query rows of the QKV buffer, or the skip tensor:
+        Block._gather_ats_skip, reference blocks.py:196-203)."""
+        if self.ats_fraction is None or self._ats_now is None:
+            return x
+        return native.gate_gather(x, self._ats_now)[0]
+
+    def _ats_dense(self, qkv):
+        """Dense attention of the kept query rows over all keys (Block / Tokenwise / Matmul1 blocks: ATS precedes the
+        matmul_2 cast, reference blocks.py:229-231,499-500)."""
+        index = self._ats_select(qkv, qkv.dtype)
+        out = native.global_attention_rows(qkv, index, self.heads, native.ATTN_DENSE,
+                                           state_dtype=self._state_dtype(qkv.dtype))
+        if self.count_mode:
+            b, n, _ = qkv.shape
+            self.matmul.counts["matmul_flops"] += b * self.heads * (n + index.shape[-1]) * n * (self.dim // self.heads)
+        return out
 
     # ------------------------------------------------------------------ shared helpers
     def _check_input(self, x):
@@ -191,6 +252,8 @@ class Block(ExtendedModule):
 
     def _dense_attention(self, qkv):
         """Block._forward_attention of the reference, fused (window partition .. recombine)."""
+        if self.ats_fraction is not None:
+            return self._ats_dense(qkv)
         b, n, _ = qkv.shape
         dh = self.dim // self.heads
         rel = self._rel_tables(qkv.dtype)
@@ -242,10 +305,10 @@ class Block(ExtendedModule):
         x = native.add(xa, xb) if xb is not None else xa
         c = self._layer_norm_all(self.input_layer_norm, x)
         attn = self._dense_attention(self.qkv(c))
-        x2 = native.add(self.projection(attn), x)
+        x2 = native.add(self.projection(attn), self._ats_rows(x))
         c2 = self._layer_norm_all(self.mlp_layer_norm, x2)
         branch = self._mlp(c2)
-        self._count_adds(x)
+        self._count_adds(x2)
         return branch, x2
 
 
@@ -351,6 +414,7 @@ class EventfulTokenwiseBlock(Block):
         qkv = self._linear(self.qkv, c1, out=self.qkv_accumulator.b, idx=index, count=count,
                            rows=self._rows_selected(index, count))
         attn = self._attention_incremental(qkv, index, count)
+        x = self._ats_rows(x)  # adaptive token sampling: the skip keeps the sampled tokens only
         # gate-accumulator 2: gate -> projection -> buffer
         _, c2, index2, count2 = self._gate_site(self.projection_gate, attn, None, None)
         proj = self._linear(self.projection, c2, out=self.projection_accumulator.b, idx=index2, count=count2,
@@ -359,7 +423,7 @@ class EventfulTokenwiseBlock(Block):
         x2, c3, index3, count3 = self._gate_site(self.mlp_gate, proj, x, self.mlp_layer_norm)
         branch = self._mlp(c3, out=self.mlp_accumulator.b, idx=index3, count=count3, rows=self._rows_selected(index3, count3))
         self._count_adds(x2)
-        assert n == x2.shape[-2]
+        assert self.ats_fraction is not None or n == x2.shape[-2]
         return branch, x2
 
     def _first_pair(self, xa, xb):
@@ -367,6 +431,7 @@ class EventfulTokenwiseBlock(Block):
         c1 = self._gate_first(self.qkv_gate, x, self.input_layer_norm)
         qkv = self._buffer_first(self.qkv_accumulator, self.qkv(c1))
         attn = self._attention_first(qkv, None)
+        x = self._ats_rows(x)
         c2 = self._gate_first(self.projection_gate, attn, None)
         proj = self._buffer_first(self.projection_accumulator, self.projection(c2))
         x2 = native.add(proj, x)
@@ -441,6 +506,11 @@ class EventfulMatmul1Block(EventfulTokenwiseBlock):
 
     def _attention_incremental(self, qkv, index, count=None):
         b, n, _ = qkv.shape
+        if self.ats_fraction is not None:  # no pooling with ATS (asserted by Block)
+            if self.count_mode:
+                self._count_matmul_1(qkv, n, None if index is None else self._rows_selected(index, count) // b,
+                                     None if index is None else self._rows_selected(index, count) // b)
+            return self._ats_dense(qkv)
         kvp, index_k, count_k = self._pooled(qkv, index, count)
         n_keys = n if kvp is None else kvp.shape[1]
         if self.count_mode:
@@ -484,12 +554,21 @@ class EventfulBlock(EventfulMatmul1Block):
         dev, sdt = qkv.device, self._state_dtype(qkv.dtype)
         kvp, _, _ = self._pooled(qkv, None, None)
         n_keys = n if kvp is None else kvp.shape[1]
+        if self.ats_fraction is not None:
+            # a and v are cast first, then sampled (reference blocks.py:561-562): the scores are formed in the state dtype;
+            # from here on the query axis of the gate state / accumulator is the sampled one
+            n = self._ats_select(qkv, sdt).shape[-1]
+            n_pad = (n + 7) // 8 * 8
         self._a_state = torch.zeros((b, h, n_keys, n_pad), dtype=sdt, device=dev)
         self._v_state = torch.empty((b, n_keys, d), dtype=sdt, device=dev)
         self._acc = torch.empty((b, n, d), dtype=sdt, device=dev)
         self._stats = torch.empty((b, h, n, 2), dtype=torch.float32, device=dev)
-        out = self._global(qkv, native.ATTN_FIRST, a_state=self._a_state, v_state=self._v_state, acc=self._acc,
-                           stats=self._stats, kv_pooled=kvp)
+        if self.ats_fraction is not None:
+            out = native.global_attention_rows(qkv, self._ats_now, h, native.ATTN_FIRST, a_state=self._a_state,
+                                               v_state=self._v_state, acc=self._acc, stats=self._stats, state_dtype=sdt)
+        else:
+            out = self._global(qkv, native.ATTN_FIRST, a_state=self._a_state, v_state=self._v_state, acc=self._acc,
+                               stats=self._stats, kv_pooled=kvp)
         self.matmul_accumulator_1.first = False
         self.v_gate.first = self.matmul_gate.first = self.matmul_accumulator_2.first = False
         self.v_gate.p = self._v_state.view(b, n_keys, h, dh).permute(0, 2, 1, 3)
@@ -510,9 +589,15 @@ class EventfulBlock(EventfulMatmul1Block):
             rows_q = self._rows_selected(index, count) // b
             cols_k = self._rows_selected(index_k, count_k) // b
             self._count_matmul_1(qkv, n_keys, rows_q, cols_k)
+            nq = self._acc.shape[1]  # query rows of the gate state: N, or the sampled rows under ATS
             self.v_gate.counts["gate_flops"] += b * h * n_keys * dh
-            self.matmul_gate.counts["gate_flops"] += b * h * n * n_keys
-            self.matmul_accumulator_2.counts["accumulator_flops"] += b * (h * cols_k * dh + 2 * h * n * dh)
-            self.matmul_accumulator_2.matmul.counts["matmul_flops"] += 2 * b * h * n * cols_k * dh
+            self.matmul_gate.counts["gate_flops"] += b * h * nq * n_keys
+            self.matmul_accumulator_2.counts["accumulator_flops"] += b * (h * cols_k * dh + 2 * h * nq * dh)
+            self.matmul_accumulator_2.matmul.counts["matmul_flops"] += 2 * b * h * nq * cols_k * dh
+        if self.ats_fraction is not None:
+            self._ats_select(qkv, self._state_dtype(qkv.dtype))
+            return native.global_attention_rows(qkv, self._ats_now, h, native.ATTN_DELTA, idx=index_k, count=count_k,
+                                                a_state=self._a_state, v_state=self._v_state, acc=self._acc,
+                                                stats=self._stats, state_dtype=self._state_dtype(qkv.dtype))
         return self._global(qkv, native.ATTN_DELTA, idx=index_k, count=count_k, a_state=self._a_state,
                             v_state=self._v_state, acc=self._acc, stats=self._stats, kv_pooled=kvp)

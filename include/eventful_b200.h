@@ -195,6 +195,31 @@ int et_global_attention(const void* qkv, const void* kv_pooled, int64_t pool_h, 
                         int64_t gh, int64_t gw, int64_t heads, int64_t dh, int dtype, int state_dtype, void* stream);
 
 /*
+ * Adaptive token sampling, scoring pass (Block._adaptive_token_sampling, blocks.py:150-157): one statistics pass over the
+ * QKV buffer that also emits raw_scores[b, h, t] = softmax(q k^T / sqrt(dh))[b, h, t, 0] * |v[b, h, t]| -- the attention each
+ * token pays to the class token times the norm of its value vector -- with every factor rounded to `score_dtype` where the
+ * reference holds it in that dtype (the model dtype, or the matmul_2_cast dtype in EventfulBlock, blocks.py:561-562).
+ * The normalisation, the sum over axis -3, the top-k and the index stabilisation (blocks.py:157-176,378-391; a host-side
+ * loop in the reference too) run on the (B, H, N) scores in the host mirror.
+ *   qkv (B, N, 3*H*dh); row_stats (B, H, N, 2) float (row max, row sum); raw_scores (B, H, N) float.  No rel-pos (ATS
+ *   models carry a class token).
+ */
+int et_ats_scores(const void* qkv, int64_t B, int64_t N, int64_t heads, int64_t dh, int dtype, int score_dtype,
+                  float* row_stats, float* raw_scores, void* stream);
+
+/*
+ * et_global_attention for a subset of the query rows (adaptive token sampling: `a.gather(dim=-2, ats_indices)`,
+ * blocks.py:178-181, ahead of the A-gate / v-gate / accumulator, blocks.py:562-569): the Nq queries are the tokens
+ * q_index[b][0 .. Nq) of the QKV buffer (the stabilised ATS index), keys and values are all N tokens.
+ * a_state (B, H, N, NP) column-major with NP = Nq rounded up to 8; acc / out (B, Nq, H*dh); v_state (B, N, H*dh);
+ * idx (B, k) selects keys as in et_global_attention.  Runs on the general-precision kernels (any dtype / state dtype).
+ */
+int et_global_attention_rows(const void* qkv, const int64_t* q_index, int64_t Nq, int mode, const int64_t* idx,
+                             const int32_t* count, int64_t k, void* a_state, void* v_state, void* acc, void* out,
+                             float* row_stats, void* workspace, int64_t B, int64_t N, int64_t heads, int64_t dh, int dtype,
+                             int state_dtype, void* stream);
+
+/*
  * K/V token pooling (Block._pool_tokens, blocks.py:303-326): out (B, Nk, 2*D) = avg_pool2d of the k and v parts of
  * qkv (B, gh*gw, 3*D) over pool_h x pool_w cells (fp32 average, rounded to dtype).
  */

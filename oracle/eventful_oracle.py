@@ -486,16 +486,20 @@ class OracleBackbone:
         if frac is None:
             return a, None
         st = self._st(i, "ats")
-        if forced is not None and (i, "ats") in forced:
-            index = forced[(i, "ats")].clone()
-        else:
+        replay = forced is not None and (i, "ats") in forced
+        if not replay or self.record_free:
             raw = a[..., 0] * torch.linalg.vector_norm(v, dim=-1)
             score = raw / raw[..., 1:].sum(dim=-1, keepdim=True)
             score[..., 0] = float("inf")
             score = score.sum(dim=-3)
             n_select = int(frac * (score.shape[-1] - 1)) + 1  # :165
-            index = score.topk(n_select, sorted=False)[1].sort(dim=-1)[0]  # :168, :379
-            index = self._stabilize(st.get("last"), index)
+            free = score.topk(n_select, sorted=False)[1].sort(dim=-1)[0]  # :168, :379
+        if replay:
+            index = forced[(i, "ats")].clone()
+            if self.record_free:  # checker aid: the set the oracle would sample here, and the scores it is based on
+                self.ats_free.append((i, free, score))
+        else:
+            index = self._stabilize(st.get("last"), free)
         st["last"] = index
         self.trace.append(((i, "ats"), index))
         if index.shape[:-1] != a.shape[:1]:
@@ -635,6 +639,7 @@ class OracleBackbone:
         """
         self.trace = []
         self.free_trace = []
+        self.ats_free = []
         if self._pos is None:  # utils.py:53-67
             self._pos = sized_position_encoding(
                 self.w["position_encoding.encoding"],

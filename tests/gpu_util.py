@@ -14,7 +14,7 @@ def build_gpu_backbone(case, params, dtype=torch.bfloat16, cast=None):
     kw = syn.backbone_kwargs(case["cfg"], case["input_size"], block_class=case["block_class"],
                              windowed_class=case.get("windowed_class", "EventfulTokenwiseBlock"),
                              matmul_2_cast=cast, has_class_token=case.get("has_class_token", False),
-                             pool_size=case.get("pool_size"))
+                             pool_size=case.get("pool_size"), ats_fraction=case.get("ats_fraction"))
     if kw.get("windowed_class") is None:
         kw.pop("windowed_class", None)
     for flag in ("gate_before_ln", "stgt"):
@@ -42,6 +42,12 @@ def gpu_trace(model):
             if g is not None and getattr(g, "last_index", None) is not None:
                 out[(i, gate)] = g.last_index.detach().cpu()
     return out
+
+
+def ats_trace(model):
+    """(block, "ats") -> the stabilised adaptive-token-sampling index of the last frame (CPU int64)."""
+    return {(i, "ats"): block.last_ats_indices.detach().cpu() for i, block in enumerate(model.blocks)
+            if getattr(block, "last_ats_indices", None) is not None}
 
 
 def rounded(params, dtype):

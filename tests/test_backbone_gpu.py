@@ -4,7 +4,7 @@ import torch
 
 from cases import CASES, n_tokens
 from golden_util import case_frames, case_params, load_golden, oracle_for, subsample
-from gpu_util import (DEV, allclose_report, build_gpu_backbone, elem_err, gpu_trace, record, rel_err, rounded,
+from gpu_util import (DEV, allclose_report, ats_trace, build_gpu_backbone, elem_err, gpu_trace, record, rel_err, rounded,
                       selection_agreement)
 
 pytestmark = pytest.mark.gpu
@@ -18,7 +18,7 @@ def run_gpu(case, params, frames, graph=False):
     with torch.inference_mode():
         for x in frames:
             outs.append(model(x.to(DT).to(DEV)).float().cpu())
-            traces.append(gpu_trace(model))
+            traces.append({**gpu_trace(model), **ats_trace(model)})
     return model, outs, traces
 
 
@@ -33,7 +33,13 @@ def _compare_selections(name, t, oracle, forced, case, tag):
     stats = {}
     for key, free_index, norm in oracle.free_trace:
         stats[key] = selection_agreement(forced[key], free_index, norm, threshold=thr)
-    assert set(stats) == set(forced), f"{name} frame {t} ({tag}): gates compared {sorted(stats)} != gates run {sorted(forced)}"
+    gates_run = {key for key in forced if key[1] != "ats"}
+    assert set(stats) == gates_run, f"{name} frame {t} ({tag}): gates compared {sorted(stats)} != gates run {sorted(gates_run)}"
+    # adaptive token sampling: the CUDA path's sampled token set against the oracle's own sampling on its inputs
+    for i, free_index, score in oracle.ats_free:
+        overlap, edge = selection_agreement(forced[(i, "ats")], free_index, score)
+        differing = round((1.0 - overlap) * free_index.shape[-1])
+        assert differing <= 1 and edge <= 0.15, f"{name} frame {t} block {i}: ATS sets differ in {differing} tokens, boundary distance {edge:.3f}"
     return stats
 
 
@@ -154,7 +160,8 @@ def test_first_frame_matches_reference_fixture(name):
     assert rel_err(got, want) < 0.04
 
 
-@pytest.mark.parametrize("name", ["tiny_vitdet", "small_vitdet_b", "small_vitdet_tc", "tiny_vivit", "vitdet_b_672", "vitdet_b_1024"])
+@pytest.mark.parametrize("name", ["tiny_vitdet", "small_vitdet_b", "small_vitdet_tc", "tiny_vivit", "vitdet_b_672", "vitdet_b_1024",
+                                  "tiny_ats_eventful", "tiny_ats_dense"])
 def test_counters_match_reference_fixture(name):
     case, gold = CASES[name], load_golden(name)
     model = build_gpu_backbone(case, case_params(case), DT)

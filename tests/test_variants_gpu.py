@@ -12,7 +12,7 @@ import torch
 
 from cases import CASES
 from golden_util import case_frames, case_params, load_golden, oracle_for, subsample
-from gpu_util import DEV, allclose_report, build_gpu_backbone, elem_err, gpu_trace, record, rel_err, rounded
+from gpu_util import DEV, allclose_report, ats_trace, build_gpu_backbone, elem_err, gpu_trace, record, rel_err, rounded
 
 pytestmark = pytest.mark.gpu
 
@@ -24,7 +24,7 @@ def run_free(case, params, frames, dtype, cast=None, graph=False):
     with torch.inference_mode():
         for x in frames:
             outs.append(model(x.to(dtype).to(DEV)).float().cpu())
-            traces.append(gpu_trace(model))
+            traces.append({**gpu_trace(model), **ats_trace(model)})
     return model, outs, traces
 
 
@@ -46,6 +46,9 @@ def test_fp32_free_running_reproduces_the_reference_fixture(name):
     exact_sets, total_sets, worst_overlap, flipped = 0, 0, 1.0, False
     for t in range(case["frames"]):
         for (i, gate), idx in traces[t].items():
+            if gate == "ats":  # adaptive token sampling: the stabilised index, slot by slot
+                assert np.array_equal(idx.numpy(), gold[f"ats_{t}_{i}"]), f"{name} frame {t} block {i}: ATS index differs"
+                continue
             want = gold[f"idx_{t}_{i}_{gate}"]
             got = np.sort(idx.numpy(), axis=-1)
             total_sets += 1
@@ -58,7 +61,7 @@ def test_fp32_free_running_reproduces_the_reference_fixture(name):
                 b = set(want.reshape(-1, want.shape[-1])[r].tolist())
                 overlap = len(a & b) / max(1, max(len(a), len(b)))
                 worst_overlap = min(worst_overlap, overlap)
-        n_gold = sum(1 for f in gold.files if f.startswith(f"idx_{t}_"))
+        n_gold = sum(1 for f in gold.files if f.startswith(f"idx_{t}_") or f.startswith(f"ats_{t}_"))
         assert len(traces[t]) == n_gold, f"{name} frame {t}: {len(traces[t])} gates traced, fixture has {n_gold}"
         want = torch.from_numpy(gold[f"out_{t}"])
         got = subsample(outs[t]) if case.get("subsample") else outs[t]
@@ -71,7 +74,8 @@ def test_fp32_free_running_reproduces_the_reference_fixture(name):
 
 
 @pytest.mark.parametrize("name,model_dtype", [("tiny_cast", torch.float32), ("small_cast16", torch.float32),
-                                              ("small_cast16", torch.bfloat16)])
+                                              ("small_cast16", torch.bfloat16), ("tiny_ats_cast16", torch.float32),
+                                              ("tiny_ats_cast16", torch.bfloat16)])
 def test_matmul_2_cast_differs_from_model_dtype(name, model_dtype):
     """
     a, v, the v-gate / A-gate state and the accumulator live in the cast dtype, q k^T and the softmax in the model dtype
