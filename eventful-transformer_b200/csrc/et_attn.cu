@@ -15,7 +15,7 @@
 
 #include "et_common.cuh"
 
-int et_tc_global_attention(const void* qkv, const void* sel, void* onehot, const void* bias_h, const void* bias_w, int mode,
+int et_tc_global_attention(const void* qkv, const void* sel, void* onehot, void* onehot_all, const void* bias_h, const void* bias_w, int mode,
                            const long long* idx, int k, void* a_state, void* acc, void* out, float* stats, int B, int N,
                            int NP, int H, int gh, int gw, int is_bf16, cudaStream_t stream);
 int et_tc_window_attention(const void* qkv, const void* pad_token, void* bias_comb, void* out, int B, int N, int gh, int gw,
@@ -867,8 +867,9 @@ template <typename T, int DH>
 int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_state, void* ws, cudaStream_t s) {
     AttnArgs args = a;
     const int D = a.H * DH;
-    // tensor-core path: dh = 64, 128-row query blocks, rel-pos bias only for the 64-wide grid
-    const bool use_tc = DH == 64 && a.N % 128 == 0 && (rel_y == nullptr || (a.gw == 64 && a.gh <= 64)) && g_attn_tc &&
+    // tensor-core path: dh = 64, at least one full 128-row query block (ragged blocks / tiles are masked), rel-pos bias
+    // for token grids up to 64 x 64 (one-hot key coordinates are 64 + 64 columns of the augmented operands)
+    const bool use_tc = DH == 64 && a.N >= 128 && (rel_y == nullptr || (a.gw <= 64 && a.gh <= 64)) && g_attn_tc &&
                         a.count == nullptr;  // a device-side key count runs on the mma.sync kernels
     // workspace layout: [bias_h | bias_w | K_sel | dV | Vd | onehot]; the tc path pads bias rows to 64 columns
     const size_t ldh = use_tc ? 64 : a.gh, ldw = use_tc ? 64 : a.gw;
@@ -878,6 +879,7 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     T* dV = Ksel + (size_t)a.B * a.k * D;
     T* Vd = dV + (size_t)a.B * a.k * D;
     T* onehot = Vd + (size_t)a.B * a.k * D;
+    T* onehot_all = onehot + (size_t)((long long)a.B * a.k > a.N ? (long long)a.B * a.k : a.N) * 128;
     if (rel_y != nullptr) {
         et_launch(relpos_bias_kernel<T, DH>, dim3(dim3(a.gh + a.gw, a.H, a.B)), dim3(kAttnThreads), 0, s, a, static_cast<const T*>(rel_y), static_cast<const T*>(rel_x), bh, bw, use_tc ? 64 : 0, use_tc ? 8.f : 1.f, 0, 0);
         ET_COUNT_LAUNCH(1);
@@ -902,7 +904,7 @@ int run_global(const AttnArgs& a, const void* rel_y, const void* rel_x, void* v_
     }
     if (use_tc) {
         if (a.mode == ET_ATTN_DELTA && a.k == 0) return ET_OK;
-        return et_tc_global_attention(a.qkv, Ksel, onehot, args.bias_h, args.bias_w, a.mode, a.idx, a.k, a.a_state, a.acc, a.out,
+        return et_tc_global_attention(a.qkv, Ksel, onehot, onehot_all, args.bias_h, args.bias_w, a.mode, a.idx, a.k, a.a_state, a.acc, a.out,
                                       a.stats, a.B, a.N, a.NP, a.H, a.gh, a.gw, std::is_same_v<T, __nv_bfloat16> ? 1 : 0, s);
     }
     const dim3 grid((a.N + BQ - 1) / BQ, a.H, a.B);
@@ -954,7 +956,7 @@ int64_t et_attn_workspace_bytes(int64_t B, int64_t N, int64_t gh, int64_t gw, in
         // upper bound over both layouts (the tensor-core path pads bias rows to 64 columns and adds a one-hot scratch)
         if (has_relpos) elems += align8(B * heads * N * (gh > 64 ? gh : 64)) + align8(B * heads * N * (gw > 64 ? gw : 64));
         elems += 3 * align8(B * k * heads * dh);
-        elems += ((B * k > N) ? B * k : N) * 128;
+        elems += ((B * k > N) ? B * k : N) * 128 + N * 128;  // one-hot key coordinates: selected keys, and all keys
         extra = B * heads * N * 2 * 4;  // statistics of the small single-window case
     }
     return elems * 2 + extra + 512;

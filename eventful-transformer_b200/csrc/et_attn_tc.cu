@@ -28,6 +28,8 @@
 // warps 2-9 = softmax: two warps per TMEM lane quarter, each thread owns one query row and half of the tile's key
 // columns.  tc_apply (576 threads): the same plus eight state-mover warps (2, 3, 12-17) that own all A-gate state
 // traffic; its softmax / epilogue warps are 4-11.
+#include <type_traits>
+
 #include "et_tcgen05.cuh"
 
 using namespace et_tc;
@@ -101,18 +103,34 @@ constexpr int ST_TILE = ST_KEYS * 64 * 2;  // 16 KB
 constexpr int ST_PARTS = 4;                   // softmax warps per TMEM lane quarter (column parts of a 64-wide image row)
 constexpr int ST_PW = 64 / ST_PARTS;          // columns per part
 constexpr int kStThreads = 64 + ST_PARTS * 128;
-constexpr int ST_OFF_X = QROWS * 128 + ST_STAGES * ST_TILE;  // (m2, l) exchange between the column parts
-constexpr int ST_SMEM = ST_OFF_X + (ST_PARTS - 1) * QROWS * 8 + 256 + 1024;
+// GEN = false: no rel-pos bias, or a 64-wide token grid (a 128-key tile = two image rows: the bias sits in registers).
+// GEN = true : any grid up to 64 x 64: the bias comes out of the MMA as in tc_apply, S' = [q | 8 bias_h | 8 bias_w] .
+//              [k | onehot(ky) | onehot(kx)]^T, three 64-column reduction blocks per operand (12 MMAs per tile instead of 4).
+template <bool GEN>
+struct StSmem {
+    static constexpr int NKB = GEN ? 3 : 1;
+    static constexpr int STAGES = GEN ? 3 : ST_STAGES;
+    static constexpr int Q_BYTES = NKB * QROWS * 128;
+    static constexpr int STAGE_BYTES = NKB * ST_TILE;
+    static constexpr int OFF_X = Q_BYTES + STAGES * STAGE_BYTES;  // (m2, l) exchange between the column parts
+    static constexpr int TOTAL = OFF_X + (ST_PARTS - 1) * QROWS * 8 + 256 + 1024;
+    static_assert(TOTAL <= 227 * 1024, "tc_stats shared memory");
+};
 
-template <bool BF16>
-__global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const TcArgs a) {
+// RAGGED: the token count is not a multiple of 128 (last query block / key tile partly empty: masks and clamps compiled in)
+template <bool BF16, bool GEN, bool RAGGED>
+__global__ void __launch_bounds__(kStThreads, 1)
+tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_bh,
+                const __grid_constant__ CUtensorMap tm_bw, const __grid_constant__ CUtensorMap tm_oh, const TcArgs a) {
     et_pdl_prologue();
+    using L = StSmem<GEN>;
+    constexpr int ST_STAGES = L::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* Qs = smem;
-    uint8_t* Ks = smem + QROWS * 128;
-    float2* xchg = reinterpret_cast<float2*>(smem + ST_OFF_X);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST_OFF_X + (ST_PARTS - 1) * QROWS * 8);
+    uint8_t* Ks = smem + L::Q_BYTES;
+    float2* xchg = reinterpret_cast<float2*>(smem + L::OFF_X);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_X + (ST_PARTS - 1) * QROWS * 8);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;
     uint64_t* k_empty = k_full + ST_STAGES;
@@ -122,7 +140,7 @@ __global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_co
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * QROWS, h = blockIdx.y, b = blockIdx.z;
-    const int T = a.N / ST_KEYS;
+    const int T = (a.N + ST_KEYS - 1) / ST_KEYS;  // the last tile may be ragged: its columns >= N are masked below
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_qkv) : "memory");
@@ -146,15 +164,25 @@ __global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_co
     if (warp == 0) {
         if (lane == 0) {
             PF_DECL
-            mbar_expect_tx(smem_u32(q_full), QROWS * 128);
+            mbar_expect_tx(smem_u32(q_full), L::Q_BYTES);
             tma_load_2d(smem_u32(Qs), &tm_qkv, smem_u32(q_full), h * 64, b * a.N + q0);
+            if (GEN) {
+                const int brow = (b * a.H + h) * a.N + q0;
+                tma_load_2d(smem_u32(Qs + QROWS * 128), &tm_bh, smem_u32(q_full), 0, brow);
+                tma_load_2d(smem_u32(Qs + 2 * QROWS * 128), &tm_bw, smem_u32(q_full), 0, brow);
+            }
             for (int t = 0; t < T; ++t) {
                 const int s = t % ST_STAGES;
                 PF(1);
                 mbar_wait(smem_u32(&k_empty[s]), ((t / ST_STAGES) & 1) ^ 1);
                 PF(0);
-                mbar_expect_tx(smem_u32(&k_full[s]), ST_TILE);
-                tma_load_2d(smem_u32(Ks + s * ST_TILE), &tm_qkv, smem_u32(&k_full[s]), a.D + h * 64, b * a.N + t * ST_KEYS);
+                uint8_t* dst = Ks + s * L::STAGE_BYTES;
+                mbar_expect_tx(smem_u32(&k_full[s]), L::STAGE_BYTES);
+                tma_load_2d(smem_u32(dst), &tm_qkv, smem_u32(&k_full[s]), a.D + h * 64, b * a.N + t * ST_KEYS);
+                if (GEN) {  // one-hot coordinates of keys t * 128 ..: rows past N are zero-filled by the TMA unit
+                    tma_load_2d(smem_u32(dst + ST_TILE), &tm_oh, smem_u32(&k_full[s]), 0, t * ST_KEYS);
+                    tma_load_2d(smem_u32(dst + 2 * ST_TILE), &tm_oh, smem_u32(&k_full[s]), 64, t * ST_KEYS);
+                }
             }
             PF(1);
             PF_FLUSH(4);
@@ -165,7 +193,6 @@ __global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_co
             PF_DECL
             mbar_wait(smem_u32(q_full), 0);
             PF(7);
-            const uint64_t dq = umma_smem_desc(smem_u32(Qs));
             for (int t = 0; t < T; ++t) {
                 const int s = t % ST_STAGES, u = t & 1;
                 mbar_wait(smem_u32(&k_full[s]), (t / ST_STAGES) & 1);
@@ -173,10 +200,14 @@ __global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_co
                 mbar_wait(smem_u32(&s_empty[u]), ((t >> 1) & 1) ^ 1);
                 PF(1);
                 tcgen05_fence_after();
-                const uint64_t dk = umma_smem_desc(smem_u32(Ks + s * ST_TILE));
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    tcgen05_mma_f16(tmem_base + u * ST_KEYS, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc, kk > 0);
+                for (int kb = 0; kb < L::NKB; ++kb) {
+                    const uint64_t dqb = umma_smem_desc(smem_u32(Qs + kb * QROWS * 128));
+                    const uint64_t dk = umma_smem_desc(smem_u32(Ks + s * L::STAGE_BYTES + kb * ST_TILE));
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tcgen05_mma_f16(tmem_base + u * ST_KEYS, dqb + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc, kb > 0 || kk > 0);
+                }
                 tcgen05_commit(smem_u32(&k_empty[s]));
                 tcgen05_commit(smem_u32(&s_full[u]));
                 PF(2);
@@ -191,12 +222,13 @@ __global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_co
         const int part = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const size_t grow = ((size_t)b * a.H + h) * a.N + q0 + row;
+        const size_t brow = RAGGED ? ((size_t)b * a.H + h) * a.N + min(q0 + row, a.N - 1) : grow;  // clamped in a ragged query block
         // rel-pos bias of this query row (stored as 8 x bias), in the log2 domain
         const float bscale = 0.125f * kLog2e;
         float bwl[ST_PW];
         const uint16_t* bh_row = nullptr;
-        if (a.has_bias) {
-            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.bias_w) + grow * 64 + part * ST_PW);
+        if (a.has_bias && !GEN) {
+            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.bias_w) + brow * 64 + part * ST_PW);
 #pragma unroll
             for (int c = 0; c < ST_PW / 8; ++c) {
                 const uint4 u4 = src[c];
@@ -207,7 +239,7 @@ __global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_co
                     bwl[c * 8 + 2 * i + 1] = elem_to_float<BF16>((uint16_t)(w[i] >> 16)) * bscale;
                 }
             }
-            bh_row = static_cast<const uint16_t*>(a.bias_h) + grow * 64;
+            bh_row = static_cast<const uint16_t*>(a.bias_h) + brow * 64;
         } else {
 #pragma unroll
             for (int i = 0; i < ST_PW; ++i) bwl[i] = 0.f;
@@ -219,7 +251,7 @@ __global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_co
             const int u = t & 1;
             PF(3);
             float bh2[2] = {0.f, 0.f};
-            if (a.has_bias) {  // a 128-key tile spans two image rows of the 64-wide grid
+            if (a.has_bias && !GEN) {  // a 128-key tile spans two image rows of the 64-wide grid
                 const uint32_t pair = *reinterpret_cast<const uint32_t*>(bh_row + 2 * t);
                 bh2[0] = elem_to_float<BF16>((uint16_t)(pair & 0xffffu)) * bscale;
                 bh2[1] = elem_to_float<BF16>((uint16_t)(pair >> 16)) * bscale;
@@ -234,15 +266,15 @@ __global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_empty[u]));
             PF(1);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const uint32_t* v = c ? v1 : v0;
-                const float bh = bh2[c];
+            // one 64-key half of the tile; MASKED: the ragged last tile of a token count that is not a multiple of 128
+            auto half_tile = [&](auto masked_tag, const uint32_t* v, float bh, int key0) {
+                constexpr bool MASKED = decltype(masked_tag)::value;
                 float x[ST_PW];
                 float cmax = -1e30f;
 #pragma unroll
                 for (int i = 0; i < ST_PW; ++i) {
                     x[i] = fmaf(__uint_as_float(v[i]), a.c1, bwl[i]);
+                    if (MASKED && key0 + i >= a.N) x[i] = -1e30f;
                     cmax = fmaxf(cmax, x[i]);
                 }
                 // m2 is a reference exponent, not necessarily the exact row max: it only moves when exceeded by more
@@ -255,10 +287,20 @@ __global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_co
                 float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
                 for (int i = 0; i < ST_PW; i += 2) {
-                    sum0 += ex2_approx(x[i] + shift);
-                    sum1 += ex2_approx(x[i + 1] + shift);
+                    const float e0 = ex2_approx(x[i] + shift), e1 = ex2_approx(x[i + 1] + shift);
+                    // masked columns add exactly nothing (x + shift cancels to a finite number while m2 is still -1e30)
+                    sum0 += (MASKED && key0 + i >= a.N) ? 0.f : e0;
+                    sum1 += (MASKED && key0 + i + 1 >= a.N) ? 0.f : e1;
                 }
                 l += sum0 + sum1;
+            };
+            const int key0 = t * ST_KEYS + part * ST_PW;  // key of v0[0]; v1[0] is 64 keys later
+            if (RAGGED && (t + 1) * ST_KEYS > a.N) {  // warp-uniform
+                half_tile(std::true_type{}, v0, bh2[0], key0);
+                half_tile(std::true_type{}, v1, bh2[1], key0 + 64);
+            } else {
+                half_tile(std::false_type{}, v0, bh2[0], key0);
+                half_tile(std::false_type{}, v1, bh2[1], key0 + 64);
             }
             PF(2);
         }
@@ -277,8 +319,10 @@ __global__ void __launch_bounds__(kStThreads, 1) tc_stats_kernel(const __grid_co
                 const float2 ov = xchg[o * QROWS + row];
                 l += ov.y * ex2_approx(ov.x - mm);
             }
-            a.stats[grow * 2] = mm;
-            a.stats[grow * 2 + 1] = l;
+            if (!RAGGED || q0 + row < a.N) {  // rows past N of a ragged query block belong to nobody
+                a.stats[grow * 2] = mm;
+                a.stats[grow * 2 + 1] = l;
+            }
         }
     }
     tcgen05_fence_before();
@@ -323,7 +367,7 @@ constexpr int AP_IDX_MAX = 3584;                  // 14 KB: what is left of the 
 constexpr int AP_SMEM = AP_OFF_IDX + AP_IDX_MAX * 4 + 1024;
 static_assert(AP_SMEM <= 227 * 1024, "tc_apply shared memory");
 
-template <bool BF16, int MODE>
+template <bool BF16, int MODE, bool RAGGED>
 __global__ void __launch_bounds__(kApThreads, 1)
 tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                 const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bw,
@@ -401,6 +445,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (MODE != ET_ATTN_DENSE) {
             const int mt = (kWideMovers ? warp - 12 : (warp < 4 ? warp - 2 : warp - 10)) * 32 + lane;
             const int segi = mt & 15, seg = segi * 8, col0 = mt >> 4;
+            const bool row_chunk_ok = !RAGGED || q0 + seg < a.NP;  // ragged last query block: 8-row chunks past the column's NP rows do not exist
             // the index of this batch entry goes to shared memory once: every tile needs it twice per thread (prefetch and
             // write-back), and an L2 round trip per tile was 15 % of the movers' time (profiles/r1_tc_apply_roles.txt)
             int* s_idx = reinterpret_cast<int*>(smem + AP_OFF_IDX);
@@ -420,7 +465,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < MV_CPT; ++i) {
                     uint8_t* d = dst + a_chunk(col0 + MV_CSTEP * i, segi);
-                    if (tok[i] >= 0) cp_async_16(smem_u32(d), a_state + a_head + (size_t)tok[i] * a.NP + q0 + seg);
+                    if (tok[i] >= 0 && row_chunk_ok) cp_async_16(smem_u32(d), a_state + a_head + (size_t)tok[i] * a.NP + q0 + seg);
                     else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);  // ragged tile: p = 0, never garbage
                 }
                 cp_async_arrive_noinc(smem_u32(&ps_full[tt % AP_PT_STAGES]));
@@ -462,7 +507,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 PF(4);
 #pragma unroll
                 for (int i = 0; i < MV_CPT; ++i)
-                    if (tok_wb[i] >= 0)  // evict-first: the 400 MB of state columns stream through L2 once per frame
+                    if (tok_wb[i] >= 0 && row_chunk_ok)  // evict-first: the 400 MB of state columns stream through L2 once per frame
                         asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a_state + a_head + (size_t)tok_wb[i] * a.NP + q0 + seg),
                                      "r"(wb[i].x), "r"(wb[i].y), "r"(wb[i].z), "r"(wb[i].w) : "memory");
                 PF(5);
@@ -612,7 +657,8 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         float m2r[4], linvr[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const size_t g = ((size_t)b * a.H + h) * a.N + q0 + quarter * 32 + 8 * i + lr;
+            const int qr = q0 + quarter * 32 + 8 * i + lr;
+            const size_t g = ((size_t)b * a.H + h) * a.N + (RAGGED ? min(qr, a.N - 1) : qr);
             m2r[i] = a.stats[g * 2];
             linvr[i] = 1.f / a.stats[g * 2 + 1];
         }
@@ -623,10 +669,11 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint16_t* acc = static_cast<uint16_t*>(a.acc);
         uint16_t* out = static_cast<uint16_t*>(a.out);
         const size_t off = ((size_t)b * a.N + q0 + row) * a.D + h * 64 + half * 32;
+        const bool row_ok = !RAGGED || q0 + row < a.N;  // ragged last query block
         uint4 prev[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            prev[c] = (MODE == ET_ATTN_DELTA) ? *reinterpret_cast<const uint4*>(acc + off + c * 8) : make_uint4(0, 0, 0, 0);
+            prev[c] = (MODE == ET_ATTN_DELTA && row_ok) ? *reinterpret_cast<const uint4*>(acc + off + c * 8) : make_uint4(0, 0, 0, 0);
         PF_DECL
         for (int t = 0; t < T; ++t) {
             const int u = (t >> 1) & 1;                      // pair buffer
@@ -711,8 +758,10 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 w[i] = pack2_elem<BF16>(lo, hi);
             }
             const uint4 pk = make_uint4(w[0], w[1], w[2], w[3]);
-            if (MODE != ET_ATTN_DENSE) *reinterpret_cast<uint4*>(acc + off + c * 8) = pk;
-            *reinterpret_cast<uint4*>(out + off + c * 8) = pk;
+            if (row_ok) {
+                if (MODE != ET_ATTN_DENSE) *reinterpret_cast<uint4*>(acc + off + c * 8) = pk;
+                *reinterpret_cast<uint4*>(out + off + c * 8) = pk;
+            }
         }
         PF(14);
         if (lane == 0 && warp == 4) PF_FLUSH(2);
@@ -746,17 +795,19 @@ __global__ void __launch_bounds__(256) onehot_kernel(const long long* idx, uint1
 }
 
 
-template <bool BF16>
-int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, int mode, cudaStream_t s) {
+template <bool BF16, bool RAGGED>
+int launch_tc(const void* qkv, const void* sel, void* onehot, void* onehot_all, const TcArgs& a, int mode, cudaStream_t s) {
     int rc;
-    if ((rc = et_raise_smem(tc_stats_kernel<BF16>, ST_SMEM))) return rc;
-    if ((rc = et_raise_smem(tc_apply_kernel<BF16, ET_ATTN_DENSE>, AP_SMEM))) return rc;
-    if ((rc = et_raise_smem(tc_apply_kernel<BF16, ET_ATTN_FIRST>, AP_SMEM))) return rc;
-    if ((rc = et_raise_smem(tc_apply_kernel<BF16, ET_ATTN_DELTA>, AP_SMEM))) return rc;
-    CUtensorMap tm128, tm64, tmsel, tmbh, tmbw, tmoh;
+    const bool gen = a.has_bias && a.gw != 64;  // general grid: the statistics pass takes the bias from one-hot MMAs too
+    if ((rc = et_raise_smem(tc_stats_kernel<BF16, false, RAGGED>, StSmem<false>::TOTAL))) return rc;
+    if ((rc = et_raise_smem(tc_stats_kernel<BF16, true, RAGGED>, StSmem<true>::TOTAL))) return rc;
+    if ((rc = et_raise_smem(tc_apply_kernel<BF16, ET_ATTN_DENSE, RAGGED>, AP_SMEM))) return rc;
+    if ((rc = et_raise_smem(tc_apply_kernel<BF16, ET_ATTN_FIRST, RAGGED>, AP_SMEM))) return rc;
+    if ((rc = et_raise_smem(tc_apply_kernel<BF16, ET_ATTN_DELTA, RAGGED>, AP_SMEM))) return rc;
+    CUtensorMap tm128, tm64, tmsel, tmbh, tmbw, tmoh, tmoh_all;
     if ((rc = make_tmap_2d(&tm128, qkv, (long long)a.B * a.N, 3LL * a.D, 128, a.is_bf16))) return rc;
     if ((rc = make_tmap_2d(&tm64, qkv, (long long)a.B * a.N, 3LL * a.D, 64, a.is_bf16))) return rc;
-    tmbh = tmbw = tmoh = tm128;  // placeholders when there is no rel-pos bias (never dereferenced)
+    tmbh = tmbw = tmoh = tmoh_all = tm128;  // placeholders when there is no rel-pos bias (never dereferenced)
     const int oh_rows = mode == ET_ATTN_DELTA ? a.B * a.k : a.N;
     if (a.has_bias) {
         const long long brows = (long long)a.B * a.H * a.N;
@@ -766,9 +817,19 @@ int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, i
         et_launch(onehot_kernel<BF16>, dim3((oh_rows * 16 + 255) / 256), dim3(256), 0, s, mode == ET_ATTN_DELTA ? a.idx : nullptr,
                                                                         static_cast<uint16_t*>(onehot), oh_rows, a.gw);
         ET_COUNT_LAUNCH(1);
+        if (gen) {  // one-hot coordinates of ALL keys for the statistics pass (the apply pass of DELTA mode has the selected ones)
+            void* all = mode == ET_ATTN_DELTA ? onehot_all : onehot;
+            if (mode == ET_ATTN_DELTA) {
+                et_launch(onehot_kernel<BF16>, dim3((a.N * 16 + 255) / 256), dim3(256), 0, s, (const long long*)nullptr,
+                          static_cast<uint16_t*>(all), a.N, a.gw);
+                ET_COUNT_LAUNCH(1);
+            }
+            if ((rc = make_tmap_2d(&tmoh_all, all, a.N, 128, 128, a.is_bf16))) return rc;
+        }
     }
-    const dim3 grid(a.N / QROWS, a.H, a.B);
-    et_launch(tc_stats_kernel<BF16>, dim3(grid), dim3(kStThreads), ST_SMEM, s, tm128, a);
+    const dim3 grid((a.N + QROWS - 1) / QROWS, a.H, a.B);
+    if (gen) et_launch(tc_stats_kernel<BF16, true, RAGGED>, dim3(grid), dim3(kStThreads), StSmem<true>::TOTAL, s, tm128, tmbh, tmbw, tmoh_all, a);
+    else et_launch(tc_stats_kernel<BF16, false, RAGGED>, dim3(grid), dim3(kStThreads), StSmem<false>::TOTAL, s, tm128, tmbh, tmbw, tmoh_all, a);
     ET_COUNT_LAUNCH(1);
     if (g_tc_time_apply) {
         if (g_ev0 == nullptr) {
@@ -780,11 +841,11 @@ int launch_tc(const void* qkv, const void* sel, void* onehot, const TcArgs& a, i
     if (mode == ET_ATTN_DELTA) {
         if ((rc = make_tmap_2d(&tmsel, sel, 3LL * a.sel_rows, (long long)a.D, 64, a.is_bf16))) return rc;
         const int cl = (g_tc_apply_cluster > 1 && grid.x % g_tc_apply_cluster == 0) ? g_tc_apply_cluster : 1;
-        et_launch_cluster(tc_apply_kernel<BF16, ET_ATTN_DELTA>, dim3(grid), dim3(kApThreads), AP_SMEM, s, cl, tm128, tmsel, tmbh, tmbw, tmoh, a);
+        et_launch_cluster(tc_apply_kernel<BF16, ET_ATTN_DELTA, RAGGED>, dim3(grid), dim3(kApThreads), AP_SMEM, s, cl, tm128, tmsel, tmbh, tmbw, tmoh, a);
     } else if (mode == ET_ATTN_FIRST) {
-        et_launch(tc_apply_kernel<BF16, ET_ATTN_FIRST>, dim3(grid), dim3(kApThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
+        et_launch(tc_apply_kernel<BF16, ET_ATTN_FIRST, RAGGED>, dim3(grid), dim3(kApThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
     } else {
-        et_launch(tc_apply_kernel<BF16, ET_ATTN_DENSE>, dim3(grid), dim3(kApThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
+        et_launch(tc_apply_kernel<BF16, ET_ATTN_DENSE, RAGGED>, dim3(grid), dim3(kApThreads), AP_SMEM, s, tm128, tm64, tmbh, tmbw, tmoh, a);
     }
     ET_COUNT_LAUNCH(1);
     if (g_tc_time_apply) cudaEventRecord(g_ev1, s);
@@ -800,9 +861,10 @@ extern "C" float et_debug_elapsed_ms(void) {
 }
 
 // Entry used by et_global_attention (et_attn.cu) when the shape qualifies for the tensor-core path.
-// `sel` = workspace rows [K_sel | v_n | v_n - dV], each (B * k, D); `onehot` = (max(B * k, N), 128) scratch;
-// bias tables in the tc layout: (B, H, N, 64) each, holding 8 x bias, zero padded.
-int et_tc_global_attention(const void* qkv, const void* sel, void* onehot, const void* bias_h, const void* bias_w, int mode,
+// `sel` = workspace rows [K_sel | v_n | v_n - dV], each (B * k, D); `onehot` = (max(B * k, N), 128) scratch, `onehot_all` =
+// (N, 128) scratch (DELTA mode on grids that are not 64 wide); bias tables in the tc layout: (B, H, N, 64) each, holding
+// 8 x bias, zero padded.  Any N >= 128 (ragged query blocks / key tiles are masked), grids up to 64 x 64.
+int et_tc_global_attention(const void* qkv, const void* sel, void* onehot, void* onehot_all, const void* bias_h, const void* bias_w, int mode,
                            const long long* idx, int k, void* a_state, void* acc, void* out, float* stats, int B, int N,
                            int NP, int H, int gh, int gw, int is_bf16, cudaStream_t stream) {
     TcArgs a;
@@ -812,5 +874,9 @@ int et_tc_global_attention(const void* qkv, const void* sel, void* onehot, const
     a.has_bias = bias_h != nullptr;
     a.c1 = 0.125f * kLog2e;
     a.prof = g_tc_prof;
-    return is_bf16 ? launch_tc<true>(qkv, sel, onehot, a, mode, stream) : launch_tc<false>(qkv, sel, onehot, a, mode, stream);
+    const bool ragged = N % QROWS != 0;
+    if (is_bf16) return ragged ? launch_tc<true, true>(qkv, sel, onehot, onehot_all, a, mode, stream)
+                               : launch_tc<true, false>(qkv, sel, onehot, onehot_all, a, mode, stream);
+    return ragged ? launch_tc<false, true>(qkv, sel, onehot, onehot_all, a, mode, stream)
+                  : launch_tc<false, false>(qkv, sel, onehot, onehot_all, a, mode, stream);
 }

@@ -3,7 +3,7 @@
 tag=${1:-r2q}
 targets=${2:-"tests/test_attention_gpu.py tests/test_backbone_gpu.py"}
 mkdir -p gpurun_out
-timeout 900 python -m pytest $targets -m gpu -x -q -p no:cacheprovider --timeout 600 > gpurun_out/${tag}_pytest.log 2>&1
+timeout 900 python -m pytest $targets -m gpu -q -p no:cacheprovider --timeout 600 > gpurun_out/${tag}_pytest.log 2>&1
 echo "== tests: $(tail -1 gpurun_out/${tag}_pytest.log)"; grep -E "^FAILED|^ERROR" gpurun_out/${tag}_pytest.log | head
 for streams in 8 1; do
 timeout 300 python bench.py --quick --streams $streams > gpurun_out/${tag}_s${streams}.json 2> gpurun_out/${tag}_s${streams}.err
