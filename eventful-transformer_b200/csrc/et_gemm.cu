@@ -107,26 +107,30 @@ unsigned long long* g_gemm_prof = nullptr;
 #endif
 
 // GELU(x) = x Phi(x) with the exact-erf definition (torch.nn.GELU default), two elements at a time.
-// Phi(x) = 1/2 + sign(x) (1/2 - q), q = erfc(|x| / sqrt 2) / 2 by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 on erf, far
-// below the 16-bit output rounding): q = (a1 t + ... + a5 t^5) / 2 * exp(-x^2 / 2), t = 1 / (1 + p |x| / sqrt 2).
-// Packed FFMA2 / FMUL2 arithmetic plus one rcp and one ex2 per element: ~9.5 issue slots per element, against ~22 for
-// the scalar version and ~40 for libdevice's erff (which made the mlp_1 epilogue three times longer than its mainloop).
+// Phi(x) = 1/2 + sign(x) (1/2 - r / 2), r = erfc(z), z = |x| / sqrt 2, by Abramowitz-Stegun 7.1.28:
+//   erfc(z) = (1 + a1 z + ... + a6 z^6)^-16, |error| < 3e-7 (|error| of GELU < 1e-6 in fp32 arithmetic, far below the 16-bit
+//   output rounding).  Packed FFMA2 / FMUL2 arithmetic and ONE MUFU (rcp) per element: the previous form (A&S 7.1.26: rcp + ex2)
+//   needed two, and the GELU epilogue of mlp_1 was MUFU-bound (16 results/clk/SM) and longer than its mainloop could hide.
 __device__ __forceinline__ void gelu_erf2(float& a, float& b) {
-    const float kc = 0.3275911f * 0.70710678118654752440f;
-    const f32x2 t = f2_pack(rcp_approx(fmaf(fabsf(a), kc, 1.f)), rcp_approx(fmaf(fabsf(b), kc, 1.f)));
-    const f32x2 x = f2_pack(a, b);
-    f32x2 p = f2_fma(f2_pack(0.5f * 1.061405429f, 0.5f * 1.061405429f), t, f2_pack(0.5f * -1.453152027f, 0.5f * -1.453152027f));
-    p = f2_fma(p, t, f2_pack(0.5f * 1.421413741f, 0.5f * 1.421413741f));
-    p = f2_fma(p, t, f2_pack(0.5f * -0.284496736f, 0.5f * -0.284496736f));
-    p = f2_fma(p, t, f2_pack(0.5f * 0.254829592f, 0.5f * 0.254829592f));
-    p = f2_mul(p, t);
-    float ea, eb;  // exp(-x^2 / 2) = exp2(x * x * (-log2(e) / 2))
-    f2_unpack(f2_mul(f2_mul(x, f2_pack(-0.72134752044448170368f, -0.72134752044448170368f)), x), ea, eb);
-    const f32x2 q = f2_mul(p, f2_pack(ex2_approx(ea), ex2_approx(eb)));
-    float sa, sb;  // 1/2 - q, carrying the sign of x
-    f2_unpack(f2_fma(q, f2_pack(-1.f, -1.f), f2_pack(0.5f, 0.5f)), sa, sb);
+    const float kr = 0.70710678118654752440f;
+    const f32x2 z = f2_mul(f2_pack(fabsf(a), fabsf(b)), f2_pack(kr, kr));
+    f32x2 p = f2_fma(f2_pack(0.0000430638f, 0.0000430638f), z, f2_pack(0.0002765672f, 0.0002765672f));
+    p = f2_fma(p, z, f2_pack(0.0001520143f, 0.0001520143f));
+    p = f2_fma(p, z, f2_pack(0.0092705272f, 0.0092705272f));
+    p = f2_fma(p, z, f2_pack(0.0422820123f, 0.0422820123f));
+    p = f2_fma(p, z, f2_pack(0.0705230784f, 0.0705230784f));
+    p = f2_fma(p, z, f2_pack(1.f, 1.f));
+    p = f2_mul(p, p);
+    p = f2_mul(p, p);
+    p = f2_mul(p, p);
+    p = f2_mul(p, p);  // (1 + ...)^16; overflows to +inf for |x| > ~40, whose reciprocal is the correct 0
+    float pa, pb;
+    f2_unpack(p, pa, pb);
+    const f32x2 r = f2_pack(rcp_approx(pa), rcp_approx(pb));
+    float sa, sb;  // 1/2 - r/2, carrying the sign of x
+    f2_unpack(f2_fma(r, f2_pack(-0.5f, -0.5f), f2_pack(0.5f, 0.5f)), sa, sb);
     const f32x2 phi = f2_add(f2_pack(copysignf(sa, a), copysignf(sb, b)), f2_pack(0.5f, 0.5f));
-    f2_unpack(f2_mul(x, phi), a, b);
+    f2_unpack(f2_mul(f2_pack(a, b), phi), a, b);
 }
 
 template <int BLOCK_N, int STAGES, int MH>  // MH = 128-row halves per CTA tile (1 or 2): the halves share the W tile
@@ -424,8 +428,14 @@ struct PersistSmem {
     static_assert(TOTAL <= 227 * 1024, "persistent GEMM tile does not fit in shared memory");
 };
 
+// Epilogue warps of the persistent kernel: four per TMEM lane quarter (a quarter of the tile's columns each).  With two per
+// quarter the epilogue (TMEM load -> bias / GELU -> pack -> staging -> row stores) kept its warps busy 70-90 % of a tile's time
+// and the MMA issuer waited for accumulator buffers (profiles/r1_gemm_roles_persistent.txt); four per scheduler hide the
+// TMEM-load, MUFU and store latencies of each other.
+constexpr int kPersistEpiWarps = 16;
+constexpr int kPersistThreads = 64 + kPersistEpiWarps * 32;
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kPersistThreads, 1)
 linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                          const LinearArgs args) {
     et_pdl_trigger();
@@ -456,7 +466,7 @@ linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         for (int u = 0; u < 2; ++u) {
             mbar_init(smem_u32(&tmem_full[u]), 1);
-            mbar_init(smem_u32(&tmem_empty[u]), 8);
+            mbar_init(smem_u32(&tmem_empty[u]), kPersistEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -544,7 +554,8 @@ linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         et_pdl_wait();
         const int ew = warp - 2;
         const int quarter = warp & 3;
-        const int chalf = ew >> 2;
+        const int chalf = ew >> 2;  // which part of the tile's columns this warp converts
+        constexpr int CPARTS = kPersistEpiWarps / 4;
         const int row = quarter * 32 + lane;
         int* s_row = reinterpret_cast<int*>(smem + L::ROW_OFFSET);
         uint8_t* stage = smem + L::STAGE_OFFSET;
@@ -561,7 +572,7 @@ linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
         };
         load_bias(blockIdx.x);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kPersistEpiWarps * 32) : "memory");
         int it = 0;
         GPF_DECL
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -614,7 +625,7 @@ linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                 }
             };
-            constexpr int HALF_N = BLOCK_N / 2;
+            constexpr int HALF_N = BLOCK_N / CPARTS;
             const int cbeg = chalf * HALF_N;
 #pragma unroll 1
             for (int c0 = cbeg; c0 + 32 <= cbeg + HALF_N; c0 += 32) {
@@ -636,12 +647,13 @@ linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 convert(acc, cbeg + HALF_N - 16, 16);
             }
             GPF(3);
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // staging tile and row table complete, bias slice consumed
+            asm volatile("bar.sync 1, %0;" ::"n"(kPersistEpiWarps * 32) : "memory");  // staging tile and row table complete, bias slice consumed
             GPF(5);
             load_bias(tile + (int)gridDim.x);  // next tile's slice; visible after the trailing barrier
             constexpr int LPR = BLOCK_N / 8;
             constexpr int RPI = 32 / LPR > 0 ? 32 / LPR : 1;
-            constexpr int NIT = 16 / RPI;
+            constexpr int ROWS_PER_WARP = BLOCK_M / kPersistEpiWarps;
+            constexpr int NIT = ROWS_PER_WARP / RPI;
             const int sub = lane / LPR, c = lane % LPR;
             const int n = n0 + c * 8;
             // all shared-memory reads first, then the stores: one latency instead of NIT
@@ -649,14 +661,14 @@ linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             int orow[NIT];
 #pragma unroll
             for (int r_it = 0; r_it < NIT; ++r_it) {
-                const int r = ew * 16 + r_it * RPI + (sub < RPI ? sub : 0);
+                const int r = ew * ROWS_PER_WARP + r_it * RPI + (sub < RPI ? sub : 0);
                 orow[r_it] = (sub < RPI && n < args.n_feat) ? s_row[r] : -1;
                 rowv[r_it] = ld16(stage + r * L::OUT_STRIDE + (((c & ~7) | ((c ^ r) & 7)) << 4));
             }
 #pragma unroll
             for (int r_it = 0; r_it < NIT; ++r_it)
                 if (orow[r_it] >= 0) st16(out + (size_t)orow[r_it] * args.ld_out + n, rowv[r_it]);
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // staging tile and row table may be rewritten
+            asm volatile("bar.sync 1, %0;" ::"n"(kPersistEpiWarps * 32) : "memory");  // staging tile and row table may be rewritten
         }
         GPF(6);
         if (warp == 2 && lane == 0) GPF_FLUSH(2);
@@ -667,6 +679,264 @@ linear_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant of the persistent kernel (tcgen05 cta_group::2): two CTAs of a cluster -- two SMs of one TPC -- compute
+// one 256 x 256 output tile.  Each CTA stages its own 128 rows of A and HALF of the W tile (128 of the 256 output features);
+// the leader CTA's single MMA thread issues M = 256 MMAs that read A from both CTAs' shared memory and the two W halves,
+// and each CTA's tensor memory receives its 128 rows x 256 columns of the accumulator.  Per k-block a CTA therefore loads
+// 32 KB instead of 48 KB for the same 128 x 256 outputs: 64 B/clk instead of 96 B/clk of L2 -> SM ingress, which is what kept
+// the single-CTA kernel's MMA issuer waiting 35 % of the time (profiles/r1_gemm_roles_persistent.txt).
+//   full[s]       leader's barrier: TMA bytes of BOTH CTAs land on it (cp.async.bulk.tensor ... cta_group::2, barrier address
+//                 with the peer bit cleared); one arrive.expect_tx by the leader's producer
+//   empty[s]      per CTA, released by the leader's tcgen05.commit multicast to both CTAs
+//   tmem_full[u]  per CTA, same multicast commit;  tmem_empty[u]  leader's barrier, 8 + 8 epilogue warps of both CTAs arrive
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int PAIR_N = 256;
+template <int STAGES>
+struct PairSmem {
+    static constexpr int W_HALF_BYTES = (PAIR_N / 2) * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + W_HALF_BYTES;   // per CTA
+    static constexpr int OUT_STRIDE = PAIR_N * 2;
+    static constexpr int STAGE_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFFSET = STAGE_OFFSET + BLOCK_M * OUT_STRIDE;
+    static constexpr int ROW_OFFSET = BAR_OFFSET + 256;
+    static constexpr int BIAS_OFFSET = ROW_OFFSET + 512;
+    static constexpr int TOTAL = BIAS_OFFSET + 512 + 1024;
+    static_assert(TOTAL <= 227 * 1024, "pair GEMM tile does not fit in shared memory");
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load whose completion bytes are credited to the LEADER CTA's mbarrier (address with the peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the barrier at this shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const LinearArgs args) {
+    et_pdl_trigger();
+    using L = PairSmem<STAGES>;
+    constexpr int TMEM_COLS = 512;  // two 256-column accumulator buffers
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int num_k_blocks = (args.K + BLOCK_K - 1) / BLOCK_K;
+    const int n_tiles = (args.n_feat + PAIR_N - 1) / PAIR_N;
+    const int m_tiles = (args.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    const int num_tiles = n_tiles * m_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int u = 0; u < 2; ++u) {
+            mbar_init(smem_u32(&tmem_full[u]), 1);
+            mbar_init(smem_u32(&tmem_empty[u]), 16);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();  // both CTAs' barriers are initialised and the pair's tensor memory is allocated
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            et_pdl_wait();
+            int kbg = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m0 = (tile / n_tiles) * 2 * BLOCK_M + (int)rank * BLOCK_M;
+                const int n0 = (tile % n_tiles) * PAIR_N + (int)rank * (PAIR_N / 2);
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++kbg) {
+                    const int s = kbg % STAGES;
+                    mbar_wait(smem_u32(&empty_bar[s]), ((kbg / STAGES) & 1) ^ 1);
+                    const uint32_t dst = smem_u32(smem + s * L::STAGE_BYTES);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    if (rank == 0) mbar_expect_tx(fb, 2 * L::STAGE_BYTES);  // both CTAs' bytes
+                    tma_load_2d_pair(dst, &tmap_a, fb, kb * BLOCK_K, m0);
+                    tma_load_2d_pair(dst + A_TILE_BYTES, &tmap_w, fb, kb * BLOCK_K, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            uint32_t idesc = umma_idesc(PAIR_N, args.is_bf16);
+            idesc = (idesc & ~(0x1fu << 24)) | ((uint32_t)(256 >> 4) << 24);  // M = 256 across the pair
+            int kbg = 0, it = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+                const int buf = it & 1;
+                mbar_wait(smem_u32(&tmem_empty[buf]), ((it >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this buffer
+                tcgen05_fence_after();
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++kbg) {
+                    const int s = kbg % STAGES;
+                    mbar_wait(smem_u32(&full_bar[s]), (kbg / STAGES) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                    const uint64_t da = umma_smem_desc(a_addr);
+                    const uint64_t db = umma_smem_desc(a_addr + A_TILE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                        tcgen05_mma_f16_pair(tmem_base + buf * PAIR_N, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc,
+                                             (kb > 0 || kk > 0) ? 1u : 0u);
+                    tcgen05_commit_pair(smem_u32(&empty_bar[s]));
+                }
+                tcgen05_commit_pair(smem_u32(&tmem_full[buf]));
+            }
+        }
+    } else {
+        et_pdl_wait();
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int chalf = ew >> 2;
+        const int row = quarter * 32 + lane;
+        int* s_row = reinterpret_cast<int*>(smem + L::ROW_OFFSET);
+        uint8_t* stage = smem + L::STAGE_OFFSET;
+        uint8_t* stage_row = stage + row * L::OUT_STRIDE;
+        uint16_t* out = static_cast<uint16_t*>(args.out);
+        uint16_t* s_bias = reinterpret_cast<uint16_t*>(smem + L::BIAS_OFFSET);
+        auto load_bias = [&](int tile) {
+            const int t8 = ((int)threadIdx.x - 64) * 8;
+            if (args.bias != nullptr && tile < num_tiles && t8 < PAIR_N) {
+                const int ng = (tile % n_tiles) * PAIR_N + t8;
+                *reinterpret_cast<uint4*>(s_bias + t8) =
+                    ng < args.n_feat ? *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(args.bias) + ng)
+                                     : make_uint4(0, 0, 0, 0);
+            }
+        };
+        load_bias(pair);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        int it = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+            const int buf = it & 1;
+            const int m0 = (tile / n_tiles) * 2 * BLOCK_M + (int)rank * BLOCK_M, n0 = (tile % n_tiles) * PAIR_N;
+            const int m = m0 + row;
+            if (chalf == 0) {
+                bool valid = m < args.M;
+                long long out_row = m;
+                if (valid && args.idx != nullptr) {
+                    const int b = m / args.k, j = m - b * args.k;
+                    out_row = (long long)b * args.n_out_rows + args.idx[m];
+                }
+                s_row[row] = valid ? (int)out_row : -1;
+            }
+            __syncwarp();
+            mbar_wait(smem_u32(&tmem_full[buf]), (it >> 1) & 1);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * PAIR_N);
+            constexpr int HALF_N = PAIR_N / 2;
+            const int cbeg = chalf * HALF_N;
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + HALF_N; c0 += 32) {
+                uint32_t acc[32];
+                tmem_load_32x32(taddr + (uint32_t)c0, acc);
+                if (c0 + 32 == cbeg + HALF_N) {  // last read of this buffer: hand it back to the leader's MMA thread
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(smem_u32(&tmem_empty[buf]), 0);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int ng = n0 + c0 + g * 8;
+                    float y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(acc[g * 8 + i]);
+                    if (ng < args.n_feat) {
+                        if (args.bias != nullptr) {
+                            float bv[8];
+                            const uint4 braw = *reinterpret_cast<const uint4*>(s_bias + c0 + g * 8);
+                            if (args.is_bf16) unpack16<__nv_bfloat16>(braw, bv);
+                            else unpack16<__half>(braw, bv);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) y[i] += bv[i];
+                        }
+                        if (args.act == ET_ACT_GELU) {
+#pragma unroll
+                            for (int i = 0; i < 8; i += 2) gelu_erf2(y[i], y[i + 1]);
+                        }
+                    }
+                    const int c = (c0 >> 3) + g;
+                    st16(stage_row + (((c & ~7) | ((c ^ row) & 7)) << 4), args.is_bf16 ? pack16<__nv_bfloat16>(y) : pack16<__half>(y));
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // staging tile and row table complete, bias slice consumed
+            load_bias(tile + num_pairs);
+            constexpr int NIT = 16;  // a warp-wide store writes one row's 256 columns
+            const int n = n0 + lane * 8;
+            uint4 rowv[NIT];
+            int orow[NIT];
+#pragma unroll
+            for (int r_it = 0; r_it < NIT; ++r_it) {
+                const int r = ew * 16 + r_it;
+                orow[r_it] = n < args.n_feat ? s_row[r] : -1;
+                rowv[r_it] = ld16(stage + r * L::OUT_STRIDE + (((lane & ~7) | ((lane ^ r) & 7)) << 4));
+            }
+#pragma unroll
+            for (int r_it = 0; r_it < NIT; ++r_it)
+                if (orow[r_it] >= 0) st16(out + (size_t)orow[r_it] * args.ld_out + n, rowv[r_it]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();  // both CTAs are done with the pair's tensor memory and with each other's barriers
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -702,11 +972,31 @@ int launch_persistent(const void* A, const void* W, const LinearArgs& args, cuda
     if (rc) return rc;
     const long long tiles = (long long)((args.n_feat + BLOCK_N - 1) / BLOCK_N) * ((args.M + BLOCK_M - 1) / BLOCK_M);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    et_launch(linear_persistent_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kGemmThreads), L::TOTAL, stream, ta, tw, args);
+    et_launch(linear_persistent_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kPersistThreads), L::TOTAL, stream, ta, tw, args);
     ET_COUNT_LAUNCH(1);
     return ET_OK;
 }
 
+
+template <int STAGES>
+int launch_pair(const void* A, const void* W, const LinearArgs& args, cudaStream_t stream) {
+    using L = PairSmem<STAGES>;
+    int rc = et_raise_smem(linear_pair_kernel<STAGES>, L::TOTAL);
+    if (rc) return rc;
+    const int sms = et_sm_count();
+    CUtensorMap ta, tw;
+    rc = make_tmap_2d(&ta, A, args.M, args.K, BLOCK_M, args.is_bf16);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tw, W, args.n_feat, args.K, PAIR_N / 2, args.is_bf16);
+    if (rc) return rc;
+    const long long tiles = (long long)((args.n_feat + PAIR_N - 1) / PAIR_N) * ((args.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
+    const int pairs = (int)(tiles < sms / 2 ? tiles : sms / 2);
+    et_launch_cluster(linear_pair_kernel<STAGES>, dim3(2 * pairs), dim3(kGemmThreads), L::TOTAL, stream, 2, ta, tw, args);
+    ET_COUNT_LAUNCH(1);
+    return ET_OK;
+}
+
+int g_force_pair = 0;  // et_debug_set(13, 1 = CTA-pair kernel whenever it applies, 2 = never, 0 = auto)
 int g_force_persist = 0;  // et_debug_set(9, 1 = always persistent, 2 = never, 0 = auto)
 int g_force_mh = 0;  // et_debug_set(8, 1 | 2): rows per CTA tile = 128 x value (0 = auto)
 int g_force_block_n = 0;
@@ -763,6 +1053,10 @@ int et_debug_set(int key, long long value) {
     }
     if (key == 7) {
         g_gemm_prof = reinterpret_cast<unsigned long long*>(value);
+        return ET_OK;
+    }
+    if (key == 13) {
+        g_force_pair = (int)value;
         return ET_OK;
     }
     if (key == 4) {
@@ -840,6 +1134,18 @@ static int linear_impl(const void* A, const int64_t* a_idx, int64_t a_rows, void
     // 256-row CTA tiles (two 128-row accumulators sharing one W tile, one CTA per SM): a third less operand traffic from
     // L2, but no second CTA whose mainloop hides the epilogue.  Measured (profiles/r1_gemm_sweep.txt): only long-K
     // layers of multi-stream batches gain (mlp_2 at M = 16384: 84 -> 80 us); everything else keeps 128-row tiles.
+    // CTA-pair kernel (cta_group::2, 256 x 256 tiles): multi-wave problems without device-side counts / gathered operands
+    {
+        const long long pair_tiles = ((M + 255) / 256) * ((n_feat + PAIR_N - 1) / PAIR_N);
+        const bool eligible = count == nullptr && a_idx == nullptr && n_feat >= PAIR_N;
+        const bool pair = eligible && (g_force_pair ? g_force_pair == 1 : (M >= 12288 && act == ET_ACT_NONE && pair_tiles >= sms && g_force_mh == 0 && g_force_persist == 0 && g_force_block_n == 0));
+        if (pair) {
+            rc = launch_pair<4>(A, W, a, s);
+            if (rc) return rc;
+            ET_CHECK_LAUNCH("et_linear");
+            return ET_OK;
+        }
+    }
     // persistent kernel: multi-wave problems (at least two waves of 128 x 256 tiles); measured in profiles/r1_gemm_sweep.txt
     {
         const int pbn = g_force_block_n == 128 || g_force_block_n == 192 ? g_force_block_n : 256;

@@ -272,3 +272,32 @@ def test_linear_gather_rejects_fp32_and_bad_shapes():
     src = src.bfloat16()
     with pytest.raises(ValueError):
         native.linear_gather(src, idx, torch.zeros(8, 64, device=DEV, dtype=torch.bfloat16), None, state=torch.zeros(1, 8, 64, device=DEV, dtype=torch.bfloat16))
+
+
+def test_linear_cta_pair_kernel():
+    """The cta_group::2 kernel (two CTAs of a cluster per 256 x 256 tile, W split across the pair, M = 256 MMAs issued by the
+    leader), forced for every shape: fewer tiles than CTA pairs, many tiles per pair, ragged M / N tails, GELU, long K,
+    scatter epilogue, repeated launches (barrier phases / double-buffered tensor memory across tiles)."""
+    dtype = torch.bfloat16
+    lib = native.lib()
+    try:
+        lib.et_debug_set(13, 1)
+        for m, k, f in [(2048, 768, 2304), (257, 72, 264), (300, 64, 256), (640, 3072, 768), (16384, 768, 3072),
+                        (16384, 3072, 768), (5000, 768, 2304), (16384, 768, 768)]:
+            x, w, b = make(m, k, f, dtype, seed=m + f)
+            for _ in range(2):
+                check(native.linear(x, w, b), reference(x, w, b, 0), dtype)
+            check(native.linear(x, w, None, act=1), reference(x, w, None, 1), dtype)
+        x, w, b = make(1000, 768, 768, torch.float16, seed=2)
+        check(native.linear(x, w, b), reference(x, w, b, 0), torch.float16)
+        batch, n, k_sel, kdim, f = 8, 4096, 2048, 768, 768
+        x, w, b = make(batch * k_sel, kdim, f, dtype, seed=9)
+        idx = torch.stack([torch.randperm(n, generator=torch.Generator().manual_seed(5 + i))[:k_sel] for i in range(batch)]).to(DEV)
+        buf = torch.full((batch, n, f), 7.0, dtype=dtype, device=DEV)
+        native.linear(x.view(batch, k_sel, kdim), w, b, out=buf, idx=idx)
+        lib.et_debug_set(13, 2)
+        want = torch.full((batch, n, f), 7.0, dtype=dtype, device=DEV)
+        native.linear(x.view(batch, k_sel, kdim), w, b, out=want, idx=idx)
+        assert torch.equal(buf, want)  # same products in the same order: bit-identical to the single-CTA kernels
+    finally:
+        lib.et_debug_set(13, 0)
