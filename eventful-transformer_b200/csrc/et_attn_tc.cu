@@ -102,6 +102,17 @@ constexpr int ST_STAGES = 4;
 constexpr int ST_TILE = ST_KEYS * 64 * 2;  // 16 KB
 constexpr int ST_PARTS = 4;                   // softmax warps per TMEM lane quarter (column parts of a 64-wide image row)
 constexpr int ST_PW = 64 / ST_PARTS;          // columns per part
+// Key pairs (of the 8 per thread and 64-key half tile) whose exp2 runs on the FMA pipe; -1 = the scalar MUFU-only form.
+#ifndef ET_STATS_SW_PAIRS
+#define ET_STATS_SW_PAIRS 0
+#endif
+constexpr int ST_SW_PAIRS = ET_STATS_SW_PAIRS;
+// S tile buffers in tensor memory (128 columns each): 2 or 4
+#ifndef ET_STATS_SBUFS
+#define ET_STATS_SBUFS 2
+#endif
+constexpr int ST_SBUFS = ET_STATS_SBUFS;
+constexpr int ST_SBUF_LOG = ST_SBUFS == 4 ? 2 : 1;
 constexpr int kStThreads = 64 + ST_PARTS * 128;
 // GEN = false: no rel-pos bias, or a 64-wide token grid (a 128-key tile = two image rows: the bias sits in registers).
 // GEN = true : any grid up to 64 x 64: the bias comes out of the MMA as in tc_apply, S' = [q | 8 bias_h | 8 bias_w] .
@@ -135,8 +146,8 @@ tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     uint64_t* k_full = bars + 1;
     uint64_t* k_empty = k_full + ST_STAGES;
     uint64_t* s_full = k_empty + ST_STAGES;
-    uint64_t* s_empty = s_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
+    uint64_t* s_empty = s_full + ST_SBUFS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + ST_SBUFS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * QROWS, h = blockIdx.y, b = blockIdx.z;
@@ -149,13 +160,13 @@ tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             mbar_init(smem_u32(&k_full[s]), 1);
             mbar_init(smem_u32(&k_empty[s]), 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < ST_SBUFS; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
             mbar_init(smem_u32(&s_empty[s]), ST_PARTS * 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), ST_SBUFS * ST_KEYS);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -194,10 +205,10 @@ tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             mbar_wait(smem_u32(q_full), 0);
             PF(7);
             for (int t = 0; t < T; ++t) {
-                const int s = t % ST_STAGES, u = t & 1;
+                const int s = t % ST_STAGES, u = t & (ST_SBUFS - 1);
                 mbar_wait(smem_u32(&k_full[s]), (t / ST_STAGES) & 1);
                 PF(0);
-                mbar_wait(smem_u32(&s_empty[u]), ((t >> 1) & 1) ^ 1);
+                mbar_wait(smem_u32(&s_empty[u]), ((t >> ST_SBUF_LOG) & 1) ^ 1);
                 PF(1);
                 tcgen05_fence_after();
 #pragma unroll
@@ -246,17 +257,21 @@ tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
         float m2 = -1e30f, l = 0.f;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // the row's bias_h pair of the NEXT tile is fetched one tile ahead: loaded at the point of use, its L2 round trip was
+        // 20 % of the kernel's stall samples (gpurun_out/r2_stats.ncu-rep, long_scoreboard at the conversion below)
+        uint32_t pair_next = (a.has_bias && !GEN) ? *reinterpret_cast<const uint32_t*>(bh_row) : 0u;
         PF_DECL
         for (int t = 0; t < T; ++t) {
-            const int u = t & 1;
+            const int u = t & (ST_SBUFS - 1);
             PF(3);
             float bh2[2] = {0.f, 0.f};
             if (a.has_bias && !GEN) {  // a 128-key tile spans two image rows of the 64-wide grid
-                const uint32_t pair = *reinterpret_cast<const uint32_t*>(bh_row + 2 * t);
+                const uint32_t pair = pair_next;
+                if (t + 1 < T) pair_next = *reinterpret_cast<const uint32_t*>(bh_row + 2 * (t + 1));
                 bh2[0] = elem_to_float<BF16>((uint16_t)(pair & 0xffffu)) * bscale;
                 bh2[1] = elem_to_float<BF16>((uint16_t)(pair >> 16)) * bscale;
             }
-            mbar_wait(smem_u32(&s_full[u]), (t >> 1) & 1);
+            mbar_wait(smem_u32(&s_full[u]), (t >> ST_SBUF_LOG) & 1);
             PF(0);
             tcgen05_fence_after();
             uint32_t v0[ST_PW], v1[ST_PW];
@@ -269,6 +284,60 @@ tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             // one 64-key half of the tile; MASKED: the ragged last tile of a token count that is not a multiple of 128
             auto half_tile = [&](auto masked_tag, const uint32_t* v, float bh, int key0) {
                 constexpr bool MASKED = decltype(masked_tag)::value;
+                if constexpr (!MASKED && ST_SW_PAIRS >= 0) {
+                    // Packed fp32 arithmetic (two keys per FFMA2 / FADD2 issue slot), and exp2 of ST_SW_PAIRS of the eight key
+                    // pairs computed on the FMA pipe instead of the MUFU: the statistics pass is bound by the 16 exp2 / clk / SM
+                    // of the MUFU (1 024 cycles per 128 x 128 tile), while the FMA pipe has issue slots to spare.
+                    //   2^x = 2^n 2^r, n = round(x) by the magic-number add, r = x - n in [-1/2, 1/2], 2^r by a cubic (relative
+                    //   error < 7.5e-5, only the row sums l are formed from these values), 2^n by an integer add to the exponent.
+                    f32x2 xp[ST_PW / 2];
+                    float cmax = -1e30f;
+                    const f32x2 c1c1 = f2_pack(a.c1, a.c1);
+#pragma unroll
+                    for (int j = 0; j < ST_PW / 2; ++j) {
+                        xp[j] = f2_fma(f2_pack(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), c1c1,
+                                       f2_pack(bwl[2 * j], bwl[2 * j + 1]));
+                        float x0, x1;
+                        f2_unpack(xp[j], x0, x1);
+                        cmax = fmaxf(cmax, fmaxf(x0, x1));
+                    }
+                    if (cmax + bh > m2 + 8.f) {
+                        l *= ex2_approx(m2 - (cmax + bh));
+                        m2 = cmax + bh;
+                    }
+                    const float shift = bh - m2;
+                    const f32x2 shift2 = f2_pack(shift, shift);
+                    f32x2 sum2 = f2_pack(0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < ST_PW / 2; ++j) {
+                        const f32x2 xs = f2_add(xp[j], shift2);
+                        float x0, x1, e0, e1;
+                        f2_unpack(xs, x0, x1);
+                        if (j < ST_SW_PAIRS) {
+                            const f32x2 xc = f2_pack(fmaxf(x0, -125.f), fmaxf(x1, -125.f));  // keep 2^n a normal number
+                            const f32x2 magic = f2_pack(12582912.f, 12582912.f);             // 1.5 * 2^23: x + magic rounds x to an integer
+                            const f32x2 t = f2_add(xc, magic);
+                            const f32x2 nf = f2_add(t, f2_pack(-12582912.f, -12582912.f));
+                            const f32x2 r = f2_fma(nf, f2_pack(-1.f, -1.f), xc);
+                            f32x2 p = f2_fma(f2_pack(0.055171654f, 0.055171654f), r, f2_pack(0.24261113f, 0.24261113f));
+                            p = f2_fma(p, r, f2_pack(0.69326097f, 0.69326097f));
+                            p = f2_fma(p, r, f2_pack(0.99992806f, 0.99992806f));
+                            float t0, t1, p0, p1;
+                            f2_unpack(t, t0, t1);
+                            f2_unpack(p, p0, p1);
+                            e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+                            e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+                        } else {
+                            e0 = ex2_approx(x0);
+                            e1 = ex2_approx(x1);
+                        }
+                        sum2 = f2_add(sum2, f2_pack(e0, e1));
+                    }
+                    float s0, s1;
+                    f2_unpack(sum2, s0, s1);
+                    l += s0 + s1;
+                    return;
+                }
                 float x[ST_PW];
                 float cmax = -1e30f;
 #pragma unroll
@@ -329,7 +398,7 @@ tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, ST_SBUFS * ST_KEYS);
     }
 }
 
