@@ -428,11 +428,17 @@ constexpr int AP_OFF_PT = AP_OFF_ST + 2 * AP_STAGE;
 #define ET_APPLY_AN_BUFS 1
 #endif
 constexpr int AN_BUFS = ET_APPLY_AN_BUFS;
-constexpr int AP_PT_STAGES = AN_BUFS == 1 ? 4 : 3;  // a_state tiles are prefetched this many tiles ahead by the mover warps
+#ifndef ET_APPLY_PT_STAGES
+#define ET_APPLY_PT_STAGES (ET_APPLY_AN_BUFS == 1 ? 4 : 3)
+#endif
+constexpr int AP_PT_STAGES = ET_APPLY_PT_STAGES;  // a_state tiles are prefetched this many tiles ahead by the mover warps
 constexpr int AP_OFF_P = AP_OFF_PT + AP_PT_STAGES * AP_PT;
 constexpr int AP_OFF_MISC = AP_OFF_P + AN_BUFS * AP_P;
 constexpr int AP_OFF_IDX = AP_OFF_MISC + 1024;    // int32 copy of this batch entry's selected-key index (DELTA mode, k <= AP_IDX_MAX)
-constexpr int AP_IDX_MAX = 3584;                  // 14 KB: what is left of the 227 KB
+#ifndef ET_APPLY_IDX_MAX
+#define ET_APPLY_IDX_MAX 3584
+#endif
+constexpr int AP_IDX_MAX = ET_APPLY_IDX_MAX;      // 14 KB: what is left of the 227 KB
 constexpr int AP_SMEM = AP_OFF_IDX + AP_IDX_MAX * 4 + 1024;
 static_assert(AP_SMEM <= 227 * 1024, "tc_apply shared memory");
 

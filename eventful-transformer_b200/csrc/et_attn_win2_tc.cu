@@ -22,6 +22,19 @@
 
 using namespace et_tc;
 
+// Profiling build (make prof): per-phase cycle buckets of the softmax role, summed over all CTAs, into row 7 of the buffer
+// registered with et_debug_set(4, ...) (profiles/window_phases.py).
+extern unsigned long long* g_tc_prof;
+#ifdef ET_TC_PROFILE
+#define WPF_DECL long long pf_[16]; for (int i_ = 0; i_ < 16; ++i_) pf_[i_] = 0; long long pf_t_ = clock64();
+#define WPF(i) do { const long long n_ = clock64(); pf_[i] += n_ - pf_t_; pf_t_ = n_; } while (0)
+#define WPF_FLUSH() do { if (a.prof) for (int i_ = 0; i_ < 16; ++i_) atomicAdd(a.prof + 7 * 16 + i_, (unsigned long long)pf_[i_]); } while (0)
+#else
+#define WPF_DECL
+#define WPF(i)
+#define WPF_FLUSH()
+#endif
+
 namespace {
 
 constexpr int kThreads = 320;
@@ -44,6 +57,7 @@ struct Win2Args {
     const void* rel_x;      // (ww, ww, 64)
     void* out;
     int B, N, gh, gw, wh, ww, nwx, nwy, H, D, Wn, NK, hq, has_bias;
+    unsigned long long* prof;
     int inv_ww;  // (1 << 20) / ww + 1: x / ww == (x * inv_ww) >> 20 for x < 4096, ww <= 16 (no integer division in the kernel)
     float c1;
 };
@@ -104,6 +118,7 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     float* xchg = reinterpret_cast<float*>(smem + OFF_MISC + 128);  // [2 column halves][128 rows] max, then sum (2 x 1 KB)
 
+    WPF_DECL
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwin = a.nwx * a.nwy;
     auto div_ww = [&](int x) { return (x * a.inv_ww) >> 20; };
@@ -131,6 +146,7 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    WPF(0);  // prologue: barrier init, TMEM allocation, CTA sync
 
     if (warp == 0) {
         if (lane == 0) {
@@ -219,7 +235,9 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             }
         }
         // rows [Wn, NK) of K must be finite?  No: their S' columns are never read.  (V pad rows are zeroed below.)
+        WPF(1);  // E table + one-hot block
         mbar_wait(smem_u32(qk_full), 0);
+        WPF(2);  // wait: Q and K landed
         // ---- padding tokens (outside the grid) equal the qkv bias: patch the zero-filled rows (swizzled chunks)
         const bool edge = (wx + 1) * a.ww > a.gw || (wy + 1) * a.wh > a.gh;
         if (edge) {
@@ -243,11 +261,13 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(ops_ready));
+        WPF(3);  // pad patch + cp.async wait + fence + arrive
 
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         // ---- rel-pos bias of this row: column half 0 takes the y part, half 1 the x part
         if (a.has_bias) {
             mbar_wait(smem_u32(u_full), 0);
+            WPF(4);  // wait: U = Q E^T
             tcgen05_fence_after();
             uint32_t raw[32];
             tmem_load_32x32(trow + (uint32_t)(ch * 32), raw);
@@ -275,12 +295,14 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(qb_ready));
+            WPF(5);  // bias columns
         }
 
         // ---- softmax over this thread's half of the keys: columns [c_lo, c_hi)
         const int half_cols = a.NK / 2 / 8 * 8;            // multiple of 8 so that P chunks stay whole (NK = 208 -> 104)
         const int c_lo = ch ? half_cols : 0, c_hi = ch ? a.NK : half_cols;
         mbar_wait(smem_u32(s_full), 0);
+        WPF(6);  // wait: S'
         tcgen05_fence_after();
         float mx = -1e30f;
         for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
@@ -309,6 +331,7 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         xchg[ch * 128 + row] = mx;
         pair_sync(1 + quarter);
         mx = fmaxf(mx, xchg[(ch ^ 1) * 128 + row]);
+        WPF(7);  // row max
         const float m2 = mx * a.c1;
         const f32x2 c1c1 = f2_pack(a.c1, a.c1), nm2 = f2_pack(-m2, -m2);
         f32x2 sum2 = f2_pack(0.f, 0.f);
@@ -358,10 +381,12 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             f2_unpack(sum2, s0, s1);
             sum += s0 + s1;
         }
+        WPF(8);  // exp2 + P stores
         pair_sync(1 + quarter);  // both maxima have been read
         xchg[ch * 128 + row] = sum;
         // ---- V: zero the pad rows [Wn, NK) (P is zero there, but 0 x garbage must stay 0) and patch out-of-grid tokens
         mbar_wait(smem_u32(v_full), 0);
+        WPF(9);  // wait: V landed
         for (int c = st; c < (a.NK - a.Wn) * 8; c += 256)
             *reinterpret_cast<uint4*>(Vs + (a.Wn + c / 8) * 128 + (c & 7) * 16) = make_uint4(0, 0, 0, 0);
         if (edge) {
@@ -379,9 +404,11 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         if (lane == 0) mbar_arrive(smem_u32(p_ready));
         pair_sync(1 + quarter);
         sum += xchg[(ch ^ 1) * 128 + row];
+        WPF(10);  // V patch + fence + arrive
 
         // ---- epilogue: O / l -> out[b, token, h * 64 + 32 ch ...] for in-grid rows (window recombine + crop)
         mbar_wait(smem_u32(o_full), 0);
+        WPF(11);  // wait: O = P V
         tcgen05_fence_after();
         uint32_t o[32];
         tmem_load_32x32(trow + (uint32_t)(ch * 32), o);
@@ -399,11 +426,16 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             }
         }
     }
+    if (warp == 2) WPF(12);  // epilogue stores
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, 256);
+    }
+    if (warp == 2) {
+        WPF(13);  // final sync + TMEM release
+        if (lane == 0) WPF_FLUSH();
     }
 }
 
@@ -438,6 +470,7 @@ int et_tc_window2_attention(const void* qkv, const void* pad_token, const void* 
     a.nwy = (gh + wh - 1) / wh; a.nwx = (gw + ww - 1) / ww; a.H = H; a.D = H * 64; a.Wn = wh * ww;
     a.NK = (a.Wn + 15) / 16 * 16; a.hq = (wh + 1) / 2; a.has_bias = rel_y != nullptr ? 1 : 0; a.c1 = 0.125f * kLog2e;
     a.inv_ww = (1 << 20) / ww + 1;
+    a.prof = g_tc_prof;
     const int nwin = a.nwx * a.nwy;
     int rc;
     if ((rc = et_raise_smem(tc_window2_kernel<true>, SMEM_BYTES))) return rc;
