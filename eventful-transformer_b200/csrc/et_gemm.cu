@@ -749,7 +749,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
 }
 
 template <int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kPersistThreads, 1)
 linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const LinearArgs args) {
     et_pdl_trigger();
     using L = PairSmem<STAGES>;
@@ -781,7 +781,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         for (int u = 0; u < 2; ++u) {
             mbar_init(smem_u32(&tmem_full[u]), 1);
-            mbar_init(smem_u32(&tmem_empty[u]), 16);
+            mbar_init(smem_u32(&tmem_empty[u]), 2 * kPersistEpiWarps);  // the epilogue warps of both CTAs
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -842,7 +842,8 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         et_pdl_wait();
         const int ew = warp - 2;
         const int quarter = warp & 3;
-        const int chalf = ew >> 2;
+        const int chalf = ew >> 2;  // which quarter of the tile's columns this warp converts (four warps per TMEM lane quarter)
+        constexpr int CPARTS = kPersistEpiWarps / 4;
         const int row = quarter * 32 + lane;
         int* s_row = reinterpret_cast<int*>(smem + L::ROW_OFFSET);
         uint8_t* stage = smem + L::STAGE_OFFSET;
@@ -859,7 +860,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
         };
         load_bias(pair);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kPersistEpiWarps * 32) : "memory");
         int it = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
             const int buf = it & 1;
@@ -878,7 +879,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             mbar_wait(smem_u32(&tmem_full[buf]), (it >> 1) & 1);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * PAIR_N);
-            constexpr int HALF_N = PAIR_N / 2;
+            constexpr int HALF_N = PAIR_N / CPARTS;
             const int cbeg = chalf * HALF_N;
 #pragma unroll 1
             for (int c0 = cbeg; c0 < cbeg + HALF_N; c0 += 32) {
@@ -913,22 +914,22 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     st16(stage_row + (((c & ~7) | ((c ^ row) & 7)) << 4), args.is_bf16 ? pack16<__nv_bfloat16>(y) : pack16<__half>(y));
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // staging tile and row table complete, bias slice consumed
+            asm volatile("bar.sync 1, %0;" ::"n"(kPersistEpiWarps * 32) : "memory");  // staging tile and row table complete, bias slice consumed
             load_bias(tile + num_pairs);
-            constexpr int NIT = 16;  // a warp-wide store writes one row's 256 columns
+            constexpr int NIT = BLOCK_M / kPersistEpiWarps;  // a warp-wide store writes one row's 256 columns
             const int n = n0 + lane * 8;
             uint4 rowv[NIT];
             int orow[NIT];
 #pragma unroll
             for (int r_it = 0; r_it < NIT; ++r_it) {
-                const int r = ew * 16 + r_it;
+                const int r = ew * NIT + r_it;
                 orow[r_it] = n < args.n_feat ? s_row[r] : -1;
                 rowv[r_it] = ld16(stage + r * L::OUT_STRIDE + (((lane & ~7) | ((lane ^ r) & 7)) << 4));
             }
 #pragma unroll
             for (int r_it = 0; r_it < NIT; ++r_it)
                 if (orow[r_it] >= 0) st16(out + (size_t)orow[r_it] * args.ld_out + n, rowv[r_it]);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kPersistEpiWarps * 32) : "memory");
         }
     }
 
@@ -991,7 +992,7 @@ int launch_pair(const void* A, const void* W, const LinearArgs& args, cudaStream
     if (rc) return rc;
     const long long tiles = (long long)((args.n_feat + PAIR_N - 1) / PAIR_N) * ((args.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
     const int pairs = (int)(tiles < sms / 2 ? tiles : sms / 2);
-    et_launch_cluster(linear_pair_kernel<STAGES>, dim3(2 * pairs), dim3(kGemmThreads), L::TOTAL, stream, 2, ta, tw, args);
+    et_launch_cluster(linear_pair_kernel<STAGES>, dim3(2 * pairs), dim3(kPersistThreads), L::TOTAL, stream, 2, ta, tw, args);
     ET_COUNT_LAUNCH(1);
     return ET_OK;
 }
