@@ -410,7 +410,11 @@ tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #endif
 constexpr int kMoverWarps = ET_APPLY_MOVERS;
 constexpr bool kWideMovers = kMoverWarps > 8;
-constexpr int kApThreads = kWideMovers ? (12 + kMoverWarps) * 32 : (10 + kMoverWarps) * 32;  // warp 0 TMA, 1 MMA, 4-11 softmax
+// warp 0 TMA, 1 PV-MMA issuer, 4-11 softmax, movers, and one more warp that issues the S' MMAs: a tcgen05.mma occupies its
+// issuing thread ~85 cycles, and with one issuer the 12 S' MMAs of a tile pair sat between the two PV sets of the pair on the
+// critical path (softmax publish -> PV -> pv_done -> next publish); S' depends only on K' and a free S buffer
+constexpr int kSIssueWarp = kWideMovers ? 12 + kMoverWarps : 10 + kMoverWarps;
+constexpr int kApThreads = (kSIssueWarp + 1) * 32;
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int MV_CPT = 1024 / (kMoverWarps * 32);    // 16-byte chunks per mover thread and tile
@@ -652,32 +656,12 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc_s = umma_idesc_ex(128, 2 * AP_KEYS, a.is_bf16, 0);
             // PV products: A = [key][row] tiles (MN-major), B = V tiles (MN-major); the p . Vd product is subtracted
             const uint32_t idesc_o = umma_idesc_ex(128, 64, a.is_bf16, 1) | (1u << 15);
             const uint32_t idesc_neg = idesc_o | (1u << 13);  // a_negate
             PF_DECL
             mbar_wait(smem_u32(q_full), 0);
             PF(7);
-            auto issue_s = [&](int pr) {  // S' of the tile pair pr (128 keys) into pair buffer pr & 1
-                const int w = pr & 1;
-                mbar_wait(smem_u32(&k_full[0]), pr & 1);
-                PF(0);
-                mbar_wait(smem_u32(&s_empty[w]), ((pr >> 1) & 1) ^ 1);
-                PF(1);
-                tcgen05_fence_after();
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const uint64_t dq = umma_smem_desc(smem_u32(Qb(kb)));
-                    const uint64_t dk = umma_smem_desc(smem_u32(Kb(0, kb)));  // 128 key rows: tiles u = 0, 1 back to back
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        tcgen05_mma_f16(tmem_base + w * 2 * AP_KEYS, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s,
-                                        (kb > 0 || kk > 0));
-                }
-                tcgen05_commit(smem_u32(&s_full[w]));
-                tcgen05_commit(smem_u32(&k_empty[0]));
-                PF(2);
-            };
             auto issue_pv = [&](int t) {
                 const int u = t & 1;
                 mbar_wait(smem_u32(&p_ready[t % AN_BUFS]), (t / AN_BUFS) & 1);
@@ -705,13 +689,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 if (t == T - 1) tcgen05_commit(smem_u32(o_full));
                 PF(6);
             };
-            // order per pair: PV(2p), S'(p + 1), PV(2p + 1): K'(p + 1) can only be fetched once S'(p) is complete, so S'(p + 1)
-            // goes behind the first PV of the pair (its TMA round trip is hidden) and is still ready before softmax(2p + 2)
-            if (T > 0) issue_s(0);
-            for (int t = 0; t < T; ++t) {
-                issue_pv(t);
-                if ((t & 1) == 0 && t + 2 < T) issue_s((t >> 1) + 1);
-            }
+            for (int t = 0; t < T; ++t) issue_pv(t);
             PF_FLUSH(1);
         }
     } else if (warp < 4) {
@@ -840,6 +818,34 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         PF(14);
         if (lane == 0 && warp == 4) PF_FLUSH(2);
+    } else if (warp == kSIssueWarp) {
+        // ------------------------------------------------------------------ S' MMA issuer
+        if (kWideMovers) setmaxnreg_dec<56>();
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc_ex(128, 2 * AP_KEYS, a.is_bf16, 0);
+            PF_DECL
+            mbar_wait(smem_u32(q_full), 0);
+            auto issue_s = [&](int pr) {  // S' of the tile pair pr (128 keys) into pair buffer pr & 1
+                const int w = pr & 1;
+                mbar_wait(smem_u32(&k_full[0]), pr & 1);
+                PF(0);
+                mbar_wait(smem_u32(&s_empty[w]), ((pr >> 1) & 1) ^ 1);
+                PF(1);
+                tcgen05_fence_after();
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint64_t dq = umma_smem_desc(smem_u32(Qb(kb)));
+                    const uint64_t dk = umma_smem_desc(smem_u32(Kb(0, kb)));  // 128 key rows: tiles u = 0, 1 back to back
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tcgen05_mma_f16(tmem_base + w * 2 * AP_KEYS, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s,
+                                        (kb > 0 || kk > 0));
+                }
+                tcgen05_commit(smem_u32(&s_full[w]));
+                tcgen05_commit(smem_u32(&k_empty[0]));
+                PF(2);
+            };
+            for (int pr = 0; 2 * pr < T; ++pr) issue_s(pr);
+        }
     } else {
         if (kWideMovers) setmaxnreg_dec<56>();
         state_movers();
