@@ -414,7 +414,10 @@ constexpr bool kWideMovers = kMoverWarps > 8;
 // issuing thread ~85 cycles, and with one issuer the 12 S' MMAs of a tile pair sat between the two PV sets of the pair on the
 // critical path (softmax publish -> PV -> pv_done -> next publish); S' depends only on K' and a free S buffer
 constexpr int kSIssueWarp = kWideMovers ? 12 + kMoverWarps : 10 + kMoverWarps;
-constexpr int kApThreads = (kSIssueWarp + 1) * 32;
+// ... and a third issuer for the -p (v_n - dV) MMAs (DELTA mode): they need only the old state tile and V, not the softmax,
+// so they run ahead of the publish -> a_n v_n -> pv_done chain into a second accumulator that the epilogue adds
+constexpr int kPIssueWarp = kSIssueWarp + 1;
+constexpr int kApThreads = (kPIssueWarp + 1) * 32;
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int MV_CPT = 1024 / (kMoverWarps * 32);    // 16-byte chunks per mover thread and tile
@@ -492,7 +495,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_kv) : "memory");
         mbar_init(smem_u32(q_full), 1);
-        mbar_init(smem_u32(o_full), 1);
+        mbar_init(smem_u32(o_full), MODE == ET_ATTN_DELTA ? 2 : 1);  // both PV issuers commit in DELTA mode
         for (int u = 0; u < AN_BUFS; ++u) {
             mbar_init(smem_u32(&p_ready[u]), 8);
             mbar_init(smem_u32(&an_free[u]), kMoverWarps);
@@ -503,7 +506,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_init(smem_u32(&k_empty[u]), 1);
             mbar_init(smem_u32(&s_full[u]), 1);
             mbar_init(smem_u32(&s_empty[u]), 16);  // a pair buffer is drained by 8 softmax warps x 2 tiles
-            mbar_init(smem_u32(&pv_done[u]), 1);
+            mbar_init(smem_u32(&pv_done[u]), MODE == ET_ATTN_DELTA ? 2 : 1);
         }
         for (int u = 0; u < AP_PT_STAGES; ++u) mbar_init(smem_u32(&ps_full[u]), kMoverWarps * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -658,7 +661,6 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (lane == 0) {
             // PV products: A = [key][row] tiles (MN-major), B = V tiles (MN-major); the p . Vd product is subtracted
             const uint32_t idesc_o = umma_idesc_ex(128, 64, a.is_bf16, 1) | (1u << 15);
-            const uint32_t idesc_neg = idesc_o | (1u << 13);  // a_negate
             PF_DECL
             mbar_wait(smem_u32(q_full), 0);
             PF(7);
@@ -675,16 +677,6 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 for (int kk = 0; kk < 4; ++kk)  // 16 keys per step = 16 lines of 128 B (2048 B) in the A and V tiles
                     tcgen05_mma_f16(tmem_o, dan + (uint64_t)(128 * kk), dv1 + (uint64_t)(128 * kk), idesc_o, (t > 0 || kk > 0));
                 PF(4);
-                if (MODE == ET_ATTN_DELTA) {
-                    mbar_wait(smem_u32(&ps_full[t % AP_PT_STAGES]), (t / AP_PT_STAGES) & 1);  // old state tile landed
-                    PF(5);
-                    fence_proxy_async();  // cp.async (generic proxy) writes -> visible to the tensor core
-                    const uint64_t dp = umma_smem_desc_mn_a(smem_u32(Pt(t % AP_PT_STAGES)));
-                    const uint64_t dv2 = umma_smem_desc_mn(smem_u32(V2(u)));
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        tcgen05_mma_f16(tmem_o, dp + (uint64_t)(128 * kk), dv2 + (uint64_t)(128 * kk), idesc_neg, 1u);
-                }
                 tcgen05_commit(smem_u32(&pv_done[u]));
                 if (t == T - 1) tcgen05_commit(smem_u32(o_full));
                 PF(6);
@@ -792,6 +784,12 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             PF(12);
             tcgen05_fence_after();
             tmem_load_32x32(taddr + (uint32_t)(4 * AP_KEYS + half * 32), o);
+            if (MODE == ET_ATTN_DELTA) {  // second accumulator: - p (v_n - dV)
+                uint32_t o2[32];
+                tmem_load_32x32(taddr + (uint32_t)(4 * AP_KEYS + 64 + half * 32), o2);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) + __uint_as_float(o2[i]));
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = 0u;
@@ -818,6 +816,26 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         PF(14);
         if (lane == 0 && warp == 4) PF_FLUSH(2);
+    } else if (warp == kPIssueWarp) {
+        // ------------------------------------------------------------------ -p (v_n - dV) MMA issuer (DELTA mode)
+        if (kWideMovers) setmaxnreg_dec<56>();
+        if (MODE == ET_ATTN_DELTA && lane == 0) {
+            const uint32_t idesc_neg = umma_idesc_ex(128, 64, a.is_bf16, 1) | (1u << 15) | (1u << 13);  // MN-major A and B, a_negate
+            for (int t = 0; t < T; ++t) {
+                const int u = t & 1;
+                mbar_wait(smem_u32(&v_full[u]), (t >> 1) & 1);
+                mbar_wait(smem_u32(&ps_full[t % AP_PT_STAGES]), (t / AP_PT_STAGES) & 1);  // old state tile landed
+                tcgen05_fence_after();
+                fence_proxy_async();  // cp.async (generic proxy) writes -> visible to the tensor core
+                const uint64_t dp = umma_smem_desc_mn_a(smem_u32(Pt(t % AP_PT_STAGES)));
+                const uint64_t dv2 = umma_smem_desc_mn(smem_u32(V2(u)));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    tcgen05_mma_f16(tmem_o + 64, dp + (uint64_t)(128 * kk), dv2 + (uint64_t)(128 * kk), idesc_neg, (t > 0 || kk > 0));
+                tcgen05_commit(smem_u32(&pv_done[u]));
+                if (t == T - 1) tcgen05_commit(smem_u32(o_full));
+            }
+        }
     } else if (warp == kSIssueWarp) {
         // ------------------------------------------------------------------ S' MMA issuer
         if (kWideMovers) setmaxnreg_dec<56>();
