@@ -572,6 +572,8 @@ def main():
     # copies run on a second stream, double buffered, so they overlap the neighbouring frames' compute (et_pipeline)
     pipe = et_pipeline.FramePipeline(model, (args.streams, n, d), dt, dev)
 
+    e2e_warm = max(3, args.warmup)  # untimed steps through the same pipeline: staging buffers, copy stream, pinned pages
+
     def e2e_step(i):
         pipe.step(frames_host[(t_next + i) % RING], frames_host[(t_next + i + 1) % RING])
 
@@ -579,6 +581,9 @@ def main():
         torch.cuda.current_stream().wait_stream(pipe.copy_stream)
 
     with torch.inference_mode():
+        for i in range(e2e_warm):
+            e2e_step(i)
+        t_next += e2e_warm
         ms_e2e = timed_steps(e2e_step, args.steps, dist_ctx, finalize=e2e_finalize)
         out_host = pipe.flush()
     e2e_value = frames_total / (ms_e2e * 1e-3)

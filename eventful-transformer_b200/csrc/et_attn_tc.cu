@@ -403,23 +403,17 @@ tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 }
 
 // ============================================================================================= phase B
-// State-mover warps of tc_apply: 8 = warps 2-3 and 12-17 (576 threads); 16 = warps 12-27 (896 threads, warps 2-3 idle), with
-// the register file re-divided by setmaxnreg (softmax warpgroups 104, everything else 40 / 56) -- build-time experiment switch.
-#ifndef ET_APPLY_MOVERS
-#define ET_APPLY_MOVERS 8
-#endif
-constexpr int kMoverWarps = ET_APPLY_MOVERS;
-constexpr bool kWideMovers = kMoverWarps > 8;
+// State-mover warps of tc_apply: warps 2-3 and 12-17.  (Sixteen mover warps with the register file re-divided by setmaxnreg
+// were measured in round 2 and gave nothing: 623.7 vs 623.9 frames/s, profiles/r2_experiments.md.)
+constexpr int kMoverWarps = 8;
 // warp 0 TMA, 1 PV-MMA issuer, 4-11 softmax, movers, and one more warp that issues the S' MMAs: a tcgen05.mma occupies its
 // issuing thread ~85 cycles, and with one issuer the 12 S' MMAs of a tile pair sat between the two PV sets of the pair on the
 // critical path (softmax publish -> PV -> pv_done -> next publish); S' depends only on K' and a free S buffer
-constexpr int kSIssueWarp = kWideMovers ? 12 + kMoverWarps : 10 + kMoverWarps;
+constexpr int kSIssueWarp = 10 + kMoverWarps;
 // ... and a third issuer for the -p (v_n - dV) MMAs (DELTA mode): they need only the old state tile and V, not the softmax,
 // so they run ahead of the publish -> a_n v_n -> pv_done chain into a second accumulator that the epilogue adds
 constexpr int kPIssueWarp = kSIssueWarp + 1;
 constexpr int kApThreads = (kPIssueWarp + 1) * 32;
-template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int MV_CPT = 1024 / (kMoverWarps * 32);    // 16-byte chunks per mover thread and tile
 constexpr int MV_CSTEP = kMoverWarps * 2;            // columns covered by one pass of the mover threads
 constexpr int AP_KEYS = 64;
@@ -525,7 +519,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // (modules.py:200).  Scattered 256-byte HBM segments stall the issuing warps (LSU back-pressure), so this traffic
         // has its own warps and never holds up the exp / MMA pipeline.
         if (MODE != ET_ATTN_DENSE) {
-            const int mt = (kWideMovers ? warp - 12 : (warp < 4 ? warp - 2 : warp - 10)) * 32 + lane;
+            const int mt = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
             const int segi = mt & 15, seg = segi * 8, col0 = mt >> 4;
             const bool row_chunk_ok = !RAGGED || q0 + seg < a.NP;  // ragged last query block: 8-row chunks past the column's NP rows do not exist
             // the index of this batch entry goes to shared memory once: every tile needs it twice per thread (prefetch and
@@ -598,9 +592,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
     };
 
-    // Role dispatch by warpgroup, so that each setmaxnreg (16-mover build) is executed by the four warps of a warpgroup together
-    // and dominates the code it budgets: 0 = TMA / MMA (/ movers in the 8-mover build), 1-2 = softmax, 3+ = movers.
-    if (kWideMovers && warp < 4) setmaxnreg_dec<40>();
+    // Role dispatch: warp 0 TMA, 1 a_n v_n issuer, 2-3 movers, 4-11 softmax, 12-17 movers, 18 S' issuer, 19 p Vd issuer
     if (warp == 0) {
         // ------------------------------------------------------------------ producer + state write-back
         if (lane == 0) {
@@ -685,10 +677,9 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             PF_FLUSH(1);
         }
     } else if (warp < 4) {
-        if (!kWideMovers) state_movers();  // warps 2-3 (spare in the 16-mover build)
+        state_movers();  // warps 2-3
     } else if (warp < 12) {
         // ------------------------------------------------------------------ softmax / epilogue
-        if (kWideMovers) setmaxnreg_inc<104>();
         const int quarter = warp & 3;
         const int half = (warp - 4) >> 2;  // key columns [32 half, +32) of every 64-key tile
         const int row = quarter * 32 + lane;
@@ -818,7 +809,6 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (lane == 0 && warp == 4) PF_FLUSH(2);
     } else if (warp == kPIssueWarp) {
         // ------------------------------------------------------------------ -p (v_n - dV) MMA issuer (DELTA mode)
-        if (kWideMovers) setmaxnreg_dec<56>();
         if (MODE == ET_ATTN_DELTA && lane == 0) {
             const uint32_t idesc_neg = umma_idesc_ex(128, 64, a.is_bf16, 1) | (1u << 15) | (1u << 13);  // MN-major A and B, a_negate
             for (int t = 0; t < T; ++t) {
@@ -838,7 +828,6 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
     } else if (warp == kSIssueWarp) {
         // ------------------------------------------------------------------ S' MMA issuer
-        if (kWideMovers) setmaxnreg_dec<56>();
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc_ex(128, 2 * AP_KEYS, a.is_bf16, 0);
             PF_DECL
@@ -865,7 +854,6 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int pr = 0; 2 * pr < T; ++pr) issue_s(pr);
         }
     } else {
-        if (kWideMovers) setmaxnreg_dec<56>();
         state_movers();
     }
     tcgen05_fence_before();
