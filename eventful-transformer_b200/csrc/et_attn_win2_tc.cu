@@ -198,6 +198,15 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         const int ry_ = div_ww(row);
         const int ly = y0 + ry_, lx = row - ry_ * a.ww;  // window-local coordinates of the query
         const uint16_t* pad = static_cast<const uint16_t*>(a.pad_token);
+        // padding tokens equal the qkv bias: the patch loops below touch chunk (st & 7) of a row only, so every thread needs one
+        // 16-byte piece of the head's q / k / v bias -- fetched here, once, instead of inside the loops
+        const bool edge_win = (wx + 1) * a.ww > a.gw || (wy + 1) * a.wh > a.gh;
+        uint4 pad_q = make_uint4(0, 0, 0, 0), pad_k = pad_q, pad_v = pad_q;
+        if (edge_win) {
+            pad_q = *reinterpret_cast<const uint4*>(pad + h * 64 + (st & 7) * 8);
+            pad_k = *reinterpret_cast<const uint4*>(pad + a.D + h * 64 + (st & 7) * 8);
+            pad_v = *reinterpret_cast<const uint4*>(pad + 2 * a.D + h * 64 + (st & 7) * 8);
+        }
 
         // ---- operands that no TMA writes: the E table (in the V region), the one-hot key block, zero pad rows of V later
         if (a.has_bias) {
@@ -245,16 +254,14 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 const int r = c >> 3, chunk = c & 7;
                 const int ky = div_ww(r), kx = r - ky * a.ww;
                 if (wy * a.wh + ky >= a.gh || wx * a.ww + kx >= a.gw)
-                    *reinterpret_cast<uint4*>(Kk + r * 128 + ((chunk ^ (r & 7)) << 4)) =
-                        *reinterpret_cast<const uint4*>(pad + a.D + h * 64 + chunk * 8);
+                    *reinterpret_cast<uint4*>(Kk + r * 128 + ((chunk ^ (r & 7)) << 4)) = pad_k;
             }
             for (int c = st; c < nq * 8; c += 256) {    // queries of this half
                 const int r = c >> 3, chunk = c & 7;
                 const int qr = div_ww(r);
                 const int qy = y0 + qr, qx = r - qr * a.ww;
                 if (wy * a.wh + qy >= a.gh || wx * a.ww + qx >= a.gw)
-                    *reinterpret_cast<uint4*>(Qq + r * 128 + ((chunk ^ (r & 7)) << 4)) =
-                        *reinterpret_cast<const uint4*>(pad + h * 64 + chunk * 8);
+                    *reinterpret_cast<uint4*>(Qq + r * 128 + ((chunk ^ (r & 7)) << 4)) = pad_q;
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -298,6 +305,21 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             WPF(5);  // bias columns
         }
 
+        // ---- V: zero the pad rows [Wn, NK) (P is zero there, but 0 x garbage must stay 0) and patch out-of-grid tokens.  Done
+        // here, while the S' MMAs run: V has been in flight since U was read, and after the softmax only the fence remains
+        mbar_wait(smem_u32(v_full), 0);
+        WPF(9);  // wait: V landed
+        for (int c = st; c < (a.NK - a.Wn) * 8; c += 256)
+            *reinterpret_cast<uint4*>(Vs + (a.Wn + c / 8) * 128 + (c & 7) * 16) = make_uint4(0, 0, 0, 0);
+        if (edge) {
+            for (int c = st; c < a.Wn * 8; c += 256) {
+                const int r = c >> 3, chunk = c & 7;
+                const int ky = div_ww(r), kx = r - ky * a.ww;
+                if (wy * a.wh + ky >= a.gh || wx * a.ww + kx >= a.gw)
+                    *reinterpret_cast<uint4*>(Vs + r * 128 + ((chunk ^ (r & 7)) << 4)) = pad_v;
+            }
+        }
+        WPF(10);  // V patch
         // ---- softmax over this thread's half of the keys: columns [c_lo, c_hi)
         const int half_cols = a.NK / 2 / 8 * 8;            // multiple of 8 so that P chunks stay whole (NK = 208 -> 104)
         const int c_lo = ch ? half_cols : 0, c_hi = ch ? a.NK : half_cols;
@@ -384,27 +406,12 @@ tc_window2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         WPF(8);  // exp2 + P stores
         pair_sync(1 + quarter);  // both maxima have been read
         xchg[ch * 128 + row] = sum;
-        // ---- V: zero the pad rows [Wn, NK) (P is zero there, but 0 x garbage must stay 0) and patch out-of-grid tokens
-        mbar_wait(smem_u32(v_full), 0);
-        WPF(9);  // wait: V landed
-        for (int c = st; c < (a.NK - a.Wn) * 8; c += 256)
-            *reinterpret_cast<uint4*>(Vs + (a.Wn + c / 8) * 128 + (c & 7) * 16) = make_uint4(0, 0, 0, 0);
-        if (edge) {
-            for (int c = st; c < a.Wn * 8; c += 256) {
-                const int r = c >> 3, chunk = c & 7;
-                const int ky = div_ww(r), kx = r - ky * a.ww;
-                if (wy * a.wh + ky >= a.gh || wx * a.ww + kx >= a.gw)
-                    *reinterpret_cast<uint4*>(Vs + r * 128 + ((chunk ^ (r & 7)) << 4)) =
-                        *reinterpret_cast<const uint4*>(pad + 2 * a.D + h * 64 + chunk * 8);
-            }
-        }
         tcgen05_fence_before();
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(p_ready));
         pair_sync(1 + quarter);
         sum += xchg[(ch ^ 1) * 128 + row];
-        WPF(10);  // V patch + fence + arrive
 
         // ---- epilogue: O / l -> out[b, token, h * 64 + 32 ch ...] for in-grid rows (window recombine + crop)
         mbar_wait(smem_u32(o_full), 0);
