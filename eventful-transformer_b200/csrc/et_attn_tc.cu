@@ -429,6 +429,10 @@ constexpr int AP_OFF_PT = AP_OFF_ST + 2 * AP_STAGE;
 #define ET_APPLY_AN_BUFS 1
 #endif
 constexpr int AN_BUFS = ET_APPLY_AN_BUFS;
+// Two buffers were measured in round 2 (no gain: profiles/r2_experiments.md) with the single-issuer kernel.  With the softmax a
+// tile further ahead, pv_done[u] can complete twice before a mover has observed the first completion (parity aliasing), so
+// the barrier protocol below is only valid for one buffer.
+static_assert(AN_BUFS == 1, "tc_apply's pv_done protocol assumes a single a_n buffer");
 #ifndef ET_APPLY_PT_STAGES
 #define ET_APPLY_PT_STAGES (ET_APPLY_AN_BUFS == 1 ? 4 : 3)
 #endif
@@ -811,10 +815,14 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // ------------------------------------------------------------------ -p (v_n - dV) MMA issuer (DELTA mode)
         if (MODE == ET_ATTN_DELTA && lane == 0) {
             const uint32_t idesc_neg = umma_idesc_ex(128, 64, a.is_bf16, 1) | (1u << 15) | (1u << 13);  // MN-major A and B, a_negate
+            PF_DECL
             for (int t = 0; t < T; ++t) {
                 const int u = t & 1;
+                PF(2);
                 mbar_wait(smem_u32(&v_full[u]), (t >> 1) & 1);
+                PF(0);
                 mbar_wait(smem_u32(&ps_full[t % AP_PT_STAGES]), (t / AP_PT_STAGES) & 1);  // old state tile landed
+                PF(1);
                 tcgen05_fence_after();
                 fence_proxy_async();  // cp.async (generic proxy) writes -> visible to the tensor core
                 const uint64_t dp = umma_smem_desc_mn_a(smem_u32(Pt(t % AP_PT_STAGES)));
@@ -825,6 +833,8 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tcgen05_commit(smem_u32(&pv_done[u]));
                 if (t == T - 1) tcgen05_commit(smem_u32(o_full));
             }
+            PF(2);
+            PF_FLUSH(9);
         }
     } else if (warp == kSIssueWarp) {
         // ------------------------------------------------------------------ S' MMA issuer
@@ -852,6 +862,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 PF(2);
             };
             for (int pr = 0; 2 * pr < T; ++pr) issue_s(pr);
+            PF_FLUSH(8);
         }
     } else {
         state_movers();

@@ -16,8 +16,9 @@ for prm in blk.parameters(): prm.data.normal_(0, 0.02)
 qkv = torch.randn(1, n, 3 * d, device=dev).to(dt)
 ROLES = {
     0: ("producer (warp 0)", {0: "wait k_empty (S'(t-2) done)", 1: "TMA issue", 2: "wait pv_done(t-2) for V"}),
-    1: ("MMA issuer (warp 1)", {0: "wait k_full", 8: "wait v_full", 1: "wait s_empty", 2: "issue S'", 3: "wait p_ready", 4: "issue a_n.v_n",
-                                5: "wait ps_full", 6: "issue p.Vd + commit", 7: "wait q_full"}),
+    1: ("a_n.v_n MMA issuer (warp 1)", {8: "wait v_full", 3: "wait p_ready", 4: "issue a_n.v_n", 6: "commit", 7: "wait q_full"}),
+    8: ("S' MMA issuer (warp 18), per 64-key tile", {0: "wait k_full", 1: "wait s_empty", 2: "issue S' (12 MMAs per tile pair)"}),
+    9: ("p.Vd MMA issuer (warp 19)", {0: "wait v_full", 1: "wait ps_full", 2: "issue p.Vd + commit"}),
     2: ("softmax warp 4 (key half 0)", None),
     3: ("state mover (warp 2)", {0: "index loads", 1: "wait pv_done(t-1)", 2: "cp.async tile t+3", 3: "wait p_ready(t)",
                                  4: "read a_n chunks + release", 5: "state stores (STG.128)"}),
@@ -32,7 +33,7 @@ for order in ("ascending (what top-k emits)", "random"):
     blk.reset()
     blk._attention_first(qkv, None)
     for _ in range(3): blk._attention_incremental(qkv, idx)
-    prof = torch.zeros(8 * 16, dtype=torch.int64, device=dev)
+    prof = torch.zeros(12 * 16, dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
     native.lib().et_debug_set(4, prof.data_ptr())
     native.lib().et_debug_set(6, 1)
@@ -42,7 +43,7 @@ for order in ("ascending (what top-k emits)", "random"):
     native.lib().et_debug_set(4, 0)
     native.lib().et_debug_set(6, 0)
     ctas, tiles = (n // 128) * h, k // 64
-    v = prof.view(8, 16).tolist()
+    v = prof.view(12, 16).tolist()
     print(f"== index order: {order}; apply launch {ms * 1e3:.1f} us (profiling build); cycles per 64-key tile, mean over {ctas} CTAs")
     for role, (name, names) in ROLES.items():
         names = names or SM
