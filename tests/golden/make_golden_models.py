@@ -24,7 +24,7 @@ sys.modules["detectron2.structures"].ImageList = object
 sys.path.insert(0, HERE)
 sys.path.insert(0, REFERENCE)
 
-from model_cases import VIVIT_TINY, VITDET_STEM_TINY, seeded_state, vivit_video, vitdet_frames  # noqa: E402
+from model_cases import VIVIT_TINY, VIVIT_TINY_ATS, VITDET_STEM_TINY, seeded_state, vivit_video, vitdet_frames  # noqa: E402
 
 from eventful_transformer import modules as ref_modules  # noqa: E402
 from eventful_transformer import policies as ref_policies  # noqa: E402
@@ -40,8 +40,7 @@ def set_policies(model, k):
             gate.policy = ref_policies.TokenNormTopK(k=k)
 
 
-def make_vivit():
-    cfg = VIVIT_TINY
+def make_vivit(cfg=VIVIT_TINY, name="model_vivit_tiny"):
     model = ref_vivit.FactorizedViViT(**cfg["model"]).eval()
     state = seeded_state(model.state_dict(), seed=cfg["seed"])
     model.load_state_dict(state, strict=True)
@@ -53,9 +52,9 @@ def make_vivit():
         blob["probs"] = model(video).numpy()
         model.spatial_only = True
         blob["spatial"] = model(video).numpy()
-    path = os.path.join(HERE, "model_vivit_tiny.npz")
+    path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **blob)
-    print("model_vivit_tiny:", {k: v.shape for k, v in blob.items() if not k.startswith("param/")}, f"{os.path.getsize(path) / 1024:.0f} KiB")
+    print(name + ":", {k: v.shape for k, v in blob.items() if not k.startswith("param/")}, f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
 def make_vitdet_stem():
@@ -87,4 +86,5 @@ def make_vitdet_stem():
 if __name__ == "__main__":
     torch.set_num_threads(4)
     make_vivit()
+    make_vivit(VIVIT_TINY_ATS, "model_vivit_tiny_ats")
     make_vitdet_stem()

@@ -14,6 +14,23 @@ VIVIT_TINY = dict(
         temporal_stride=1, temporal_views=2, tubelet_shape=(2, 16, 16)),
 )
 
+# The EPIC-Kitchens "temporal + ATS" shape (configs/evaluate/vivit_epic_kitchens/temporal_ats_200.yml): adaptive token sampling
+# in the spatial blocks.  2 spatial x 2 temporal views are batched, and the spatial blocks have 4 heads: the reference's ATS
+# code needs batch == heads (ViViT-B: 12 views, 12 heads).  48 x 48 crops -> 3 x 3 patches + class token = 10 tokens,
+# sampled down to 7, then 5.
+VIVIT_TINY_ATS = dict(
+    seed=41, k=4,
+    video_shape=(1, 12, 3, 48, 72),
+    model=dict(
+        classes=10, input_shape=(8, 3, 48, 48), normalize_mean=0.45, normalize_std=0.225,
+        spatial_config=dict(depth=2, position_encoding_size=[3, 3], block_class="EventfulBlock",
+                            block_config=dict(dim=32, heads=4, mlp_ratio=2, ats_fraction=0.7)),
+        spatial_views=2,
+        temporal_config=dict(depth=1, position_encoding_size=[4], block_class="Block",
+                             block_config=dict(dim=32, heads=2, mlp_ratio=2)),
+        temporal_stride=1, temporal_views=2, tubelet_shape=(2, 16, 16)),
+)
+
 VITDET_STEM_TINY = dict(
     seed=37, k=6, frames=3, image_shape=(3, 50, 60),  # padded to 64 x 64 by the preprocessing
     input_shape=(3, 64, 64), normalize_mean=[123.675, 116.28, 103.53], normalize_std=[58.395, 57.12, 57.375], patch_size=16,

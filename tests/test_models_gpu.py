@@ -12,7 +12,7 @@ import et_models
 from eventful_transformer import modules, policies
 from golden_util import load_golden
 from gpu_util import DEV, record, rel_err
-from model_cases import VITDET_STEM_TINY, VIVIT_TINY
+from model_cases import VITDET_STEM_TINY, VIVIT_TINY, VIVIT_TINY_ATS
 
 pytestmark = pytest.mark.gpu
 
@@ -50,6 +50,27 @@ def test_factorized_vivit_matches_the_reference_model(dtype):
         assert err_p <= 1e-5 and err_s <= 1e-4, (err_p, err_s)
     else:
         assert err_p <= 3e-2 and abs(float(probs.sum()) - 1.0) < 1e-2, (err_p, err_s)  # selections may differ at bf16 ties
+
+
+def test_factorized_vivit_with_adaptive_token_sampling_matches_the_reference_model():
+    """The reference's FactorizedViViT with ats_fraction in the spatial blocks (the EPIC-Kitchens temporal + ATS shape, fp32):
+    4 batched views = 4 heads, 10 tokens sampled down to 7 and 5 inside the Eventful spatial sub-model, index stabilisation
+    across the 4 time steps, dense temporal sub-model on the class tokens."""
+    cfg, gold = VIVIT_TINY_ATS, load_golden("model_vivit_tiny_ats")
+    model = et_models.FactorizedViViT(**cfg["model"])
+    model.load_state_dict(_params(gold), strict=True)
+    model = model.to(DEV).eval()
+    _set_topk(model, cfg["k"])
+    video = torch.from_numpy(gold["video"]).to(DEV)
+    with torch.inference_mode():
+        probs = model(video).float().cpu()
+        model.spatial_only = True
+        spatial = model(video).float().cpu()
+    want_p, want_s = torch.from_numpy(gold["probs"]), torch.from_numpy(gold["spatial"])
+    assert probs.shape == want_p.shape and spatial.shape == want_s.shape
+    err_p, err_s = float((probs - want_p).abs().max()), rel_err(spatial, want_s)
+    record("factorized_vivit_ats_vs_reference", max_abs_prob_err=err_p, spatial_rel_err=err_s)
+    assert err_p <= 1e-5 and err_s <= 1e-4, (err_p, err_s)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
