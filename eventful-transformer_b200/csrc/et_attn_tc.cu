@@ -403,17 +403,24 @@ tc_stats_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 }
 
 // ============================================================================================= phase B
-// State-mover warps of tc_apply: warps 2-3 and 12-17.  (Sixteen mover warps with the register file re-divided by setmaxnreg
-// were measured in round 2 and gave nothing: 623.7 vs 623.9 frames/s, profiles/r2_experiments.md.)
-constexpr int kMoverWarps = 8;
+// State-mover warps of tc_apply.  8 (default): warps 2-3 and 12-17, 640 threads.  16 (-DET_APPLY_MOVERS=16): warps 12-27,
+// 1 024 threads, register file re-divided per warpgroup by setmaxnreg (softmax 104, movers 48, the rest 40).
+#ifndef ET_APPLY_MOVERS
+#define ET_APPLY_MOVERS 8
+#endif
+constexpr int kMoverWarps = ET_APPLY_MOVERS;
+constexpr bool kWideMovers = kMoverWarps == 16;
+static_assert(kMoverWarps == 8 || kMoverWarps == 16, "8 or 16 state-mover warps");
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 // warp 0 TMA, 1 PV-MMA issuer, 4-11 softmax, movers, and one more warp that issues the S' MMAs: a tcgen05.mma occupies its
 // issuing thread ~85 cycles, and with one issuer the 12 S' MMAs of a tile pair sat between the two PV sets of the pair on the
 // critical path (softmax publish -> PV -> pv_done -> next publish); S' depends only on K' and a free S buffer
-constexpr int kSIssueWarp = 10 + kMoverWarps;
+constexpr int kSIssueWarp = kWideMovers ? 28 : 10 + kMoverWarps;
 // ... and a third issuer for the -p (v_n - dV) MMAs (DELTA mode): they need only the old state tile and V, not the softmax,
 // so they run ahead of the publish -> a_n v_n -> pv_done chain into a second accumulator that the epilogue adds
 constexpr int kPIssueWarp = kSIssueWarp + 1;
-constexpr int kApThreads = (kPIssueWarp + 1) * 32;
+constexpr int kApThreads = kWideMovers ? 1024 : (kPIssueWarp + 1) * 32;
 constexpr int MV_CPT = 1024 / (kMoverWarps * 32);    // 16-byte chunks per mover thread and tile
 constexpr int MV_CSTEP = kMoverWarps * 2;            // columns covered by one pass of the mover threads
 constexpr int AP_KEYS = 64;
@@ -523,7 +530,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // (modules.py:200).  Scattered 256-byte HBM segments stall the issuing warps (LSU back-pressure), so this traffic
         // has its own warps and never holds up the exp / MMA pipeline.
         if (MODE != ET_ATTN_DENSE) {
-            const int mt = (warp < 4 ? warp - 2 : warp - 10) * 32 + lane;
+            const int mt = (kWideMovers ? warp - 12 : (warp < 4 ? warp - 2 : warp - 10)) * 32 + lane;
             const int segi = mt & 15, seg = segi * 8, col0 = mt >> 4;
             const bool row_chunk_ok = !RAGGED || q0 + seg < a.NP;  // ragged last query block: 8-row chunks past the column's NP rows do not exist
             // the index of this batch entry goes to shared memory once: every tile needs it twice per thread (prefetch and
@@ -596,8 +603,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
     };
 
-    // Role dispatch: warp 0 TMA, 1 a_n v_n issuer, 2-3 movers, 4-11 softmax, 12-17 movers, 18 S' issuer, 19 p Vd issuer
-    if (warp == 0) {
+    auto role_producer = [&]() {
         // ------------------------------------------------------------------ producer + state write-back
         if (lane == 0) {
             const int qrow = b * a.N + q0;
@@ -652,8 +658,9 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         PF(1);
         if (lane == 0) PF_FLUSH(0);
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
+    };
+    auto role_an_issuer = [&]() {
+        // ------------------------------------------------------------------ a_n . v_n MMA issuer
         if (lane == 0) {
             // PV products: A = [key][row] tiles (MN-major), B = V tiles (MN-major); the p . Vd product is subtracted
             const uint32_t idesc_o = umma_idesc_ex(128, 64, a.is_bf16, 1) | (1u << 15);
@@ -680,9 +687,8 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int t = 0; t < T; ++t) issue_pv(t);
             PF_FLUSH(1);
         }
-    } else if (warp < 4) {
-        state_movers();  // warps 2-3
-    } else if (warp < 12) {
+    };
+    auto role_softmax = [&]() {
         // ------------------------------------------------------------------ softmax / epilogue
         const int quarter = warp & 3;
         const int half = (warp - 4) >> 2;  // key columns [32 half, +32) of every 64-key tile
@@ -811,7 +817,8 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         PF(14);
         if (lane == 0 && warp == 4) PF_FLUSH(2);
-    } else if (warp == kPIssueWarp) {
+    };
+    auto role_p_issuer = [&]() {
         // ------------------------------------------------------------------ -p (v_n - dV) MMA issuer (DELTA mode)
         if (MODE == ET_ATTN_DELTA && lane == 0) {
             const uint32_t idesc_neg = umma_idesc_ex(128, 64, a.is_bf16, 1) | (1u << 15) | (1u << 13);  // MN-major A and B, a_negate
@@ -836,7 +843,8 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             PF(2);
             PF_FLUSH(9);
         }
-    } else if (warp == kSIssueWarp) {
+    };
+    auto role_s_issuer = [&]() {
         // ------------------------------------------------------------------ S' MMA issuer
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc_ex(128, 2 * AP_KEYS, a.is_bf16, 0);
@@ -864,8 +872,36 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int pr = 0; 2 * pr < T; ++pr) issue_s(pr);
             PF_FLUSH(8);
         }
+    };
+
+    if constexpr (!kWideMovers) {
+        // warp 0 TMA, 1 a_n v_n issuer, 2-3 movers, 4-11 softmax, 12-17 movers, 18 S' issuer, 19 p Vd issuer
+        if (warp == 0) role_producer();
+        else if (warp == 1) role_an_issuer();
+        else if (warp < 4) state_movers();
+        else if (warp < 12) role_softmax();
+        else if (warp == kPIssueWarp) role_p_issuer();
+        else if (warp == kSIssueWarp) role_s_issuer();
+        else state_movers();
     } else {
-        state_movers();
+        // by warpgroup, so that each setmaxnreg is executed by the four warps of a group together and dominates the code it
+        // budgets: 0 = TMA / a_n issuer, 1-2 = softmax, 3-6 = movers, 7 = S' / p issuers
+        const int wg = warp >> 2;
+        if (wg == 0) {
+            setmaxnreg_dec<40>();
+            if (warp == 0) role_producer();
+            else if (warp == 1) role_an_issuer();
+        } else if (wg <= 2) {
+            setmaxnreg_inc<104>();
+            role_softmax();
+        } else if (wg <= 6) {
+            setmaxnreg_dec<48>();
+            state_movers();
+        } else {
+            setmaxnreg_dec<40>();
+            if (warp == kSIssueWarp) role_s_issuer();
+            else if (warp == kPIssueWarp) role_p_issuer();
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
